@@ -1,0 +1,172 @@
+"""Generate the golden fixtures in this directory by EXECUTING THE REFERENCE'S OWN CODE.
+
+Run only where the reference checkout exists (this container):
+
+    python tests/golden/make_golden.py
+
+It imports, unmodified, from /root/reference (behind oracle/ref_shims.py, which supplies the
+three PyBullet math functions and an empty gym):
+
+* dronesim/control/wls_alloc.py         -> wls_cases.npz   (incl. the __main__ known answer :381-408)
+* dronesim/control/INDIControl.py       -> ctrl_<vehicle>.npz for robobee, tello, hexa_6DOF_simple
+* dronesim/control/INDIControl_6DOF.py  -> ctrl_hexa_6DOF.npz
+* dronesim/utils/math.py                -> quat_helpers.npz
+* dronesim/utils/trajGen.py             -> traj_3gates.npz (the table of examples/fly_INDI_TrajectoryTrack.py:127-160)
+
+The fixtures are small .npz files; they are what travels to the GPU box (the reference does not).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import pyb_math, ref_shims  # noqa: E402
+
+ref_shims.install()
+
+
+def rand_state_sequence(rng, n_u, T, ang_lim=1.0):
+    """A smooth random walk of T aviary state vectors (BaseAviary.py:780-790 layout)."""
+    pos = rng.uniform(-2, 2, 3)
+    rpy = rng.uniform(-ang_lim, ang_lim, 3)
+    vel = rng.normal(0, 0.5, 3)
+    angv = rng.normal(0, 0.5, 3)
+    states = np.zeros((T, 16 + n_u))
+    for t in range(T):
+        q = pyb_math.getQuaternionFromEuler(rpy)
+        states[t, 0:3] = pos
+        states[t, 3:7] = q
+        states[t, 7:10] = pyb_math.getEulerFromQuaternion(q)
+        states[t, 10:13] = vel
+        states[t, 13:16] = angv
+        pos = pos + 0.02 * vel
+        vel = vel + rng.normal(0, 0.05, 3)
+        angv = angv + rng.normal(0, 0.2, 3)
+        rpy = np.clip(rpy + 0.02 * angv, -1.3, 1.3)
+    return states
+
+
+def controller_fixture(make_ctrl, n_u, seed, T=40, n_seq=6):
+    rng = np.random.default_rng(seed)
+    out = dict(states=[], dt=[], tpos=[], tvel=[], tacc=[], trpy=[], cmd=[], pos_e=[], yaw_err=[],
+               last_vel=[], last_rates=[], last_thrust=[])
+    for s in range(n_seq):
+        ctrl = make_ctrl()
+        dt = [5 / 240, 2 / 240, 8 / 240][s % 3]
+        states = rand_state_sequence(rng, n_u, T, ang_lim=[0.3, 1.0][s % 2])
+        seq = {k: [] for k in out}
+        for t in range(T):
+            tpos = states[t, 0:3] + rng.normal(0, 0.3, 3)
+            tvel = rng.normal(0, 0.3, 3)
+            tacc = rng.normal(0, 0.3, 3)
+            trpy = np.array([0.0, 0.0, rng.uniform(-3.5, 3.5)])
+            cmd, pos_e, yaw_err = ctrl.computeControlFromState(
+                control_timestep=dt, state=states[t].copy(), target_pos=tpos, target_vel=tvel,
+                target_acc=tacc, target_rpy=trpy)
+            for k, v in (("states", states[t]), ("dt", dt), ("tpos", tpos), ("tvel", tvel), ("tacc", tacc),
+                         ("trpy", trpy), ("cmd", np.array(cmd, float)), ("pos_e", np.array(pos_e, float)),
+                         ("yaw_err", float(yaw_err)), ("last_vel", np.array(ctrl.last_vel, float)),
+                         ("last_rates", np.array(ctrl.last_rates, float)),
+                         ("last_thrust", float(ctrl.last_thrust))):
+                seq[k].append(np.array(v, dtype=np.float64))
+        for k in out:
+            out[k].append(np.array(seq[k]))
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def hover_fixture():
+    """The SURVEY 8(c) probe: robobee at rest at z=0.5, target yaw 0.4, dt=5/240."""
+    c = ref_shims.quad_controller("robobee")
+    st = np.zeros(20)
+    st[2] = 0.5
+    st[6] = 1.0
+    cmds = []
+    for _ in range(3):
+        cmd, _, _ = c.computeControlFromState(control_timestep=5 / 240, state=st,
+                                              target_pos=np.array([0, 0, 0.5]), target_rpy=np.array([0, 0, 0.4]))
+        cmds.append(np.array(cmd))
+    return np.array(cmds)
+
+
+def wls_fixture():
+    wls = ref_shims.wls_alloc()
+    # --- the reference's own known-answer case (wls_alloc.py:381-404)
+    umin = np.zeros(6)
+    umax = np.ones(6) * 9600.0
+    uc = np.array([4614, 4210, 4210, 4614, 4210, 4210], float)
+    dumin, dumax = umin - uc, umax - uc
+    v = np.array([240, -240.5658, 600.0, 1.8532])
+    Wv = np.array([100, 100, 1, 10], float)
+    A = np.array([[0.0, -0.015, 0.015, 0.0, -0.015, 0.015], [0.015, -0.010, -0.010, 0.015, -0.010, -0.010],
+                  [0.103, 0.103, 0.103, -0.103, -0.103, -0.103],
+                  [-0.0009, -0.0009, -0.0009, -0.0009, -0.0009, -0.0009]])
+    du, it = wls(v, dumin, dumax, A, None, None, Wv, None, dumin.copy())
+    kat = dict(kat_v=v, kat_umin=dumin, kat_umax=dumax, kat_B=A, kat_Wv=Wv, kat_up=dumin, kat_du=du,
+               kat_iter=it,
+               kat_matlab=np.array([-4614.0, 426.064612091305, 5390.0, -4614.0, -4210.0, 5390.0]))
+    # --- random hexa-shaped cases through the same call the 6-DOF controller makes (:607-628)
+    from dronesim_b200.vehicles import parse_urdf
+    vt = parse_urdf(os.path.join(ref_shims.REFERENCE_ROOT, "dronesim", "assets", "hexa_6DOF.urdf"))
+    B = vt.G1 / 0.05
+    Wv6 = np.array([1000, 1000, 0.1, 10, 10, 100], float)
+    rng = np.random.default_rng(7)
+    vs, cmds, dus, its, ok = [], [], [], [], []
+    for k in range(400):
+        sigma = [1.0, 10.0, 50.0, 150.0][k % 4]
+        centre = [0.5, 0.95, 0.05, 0.5][(k // 4) % 4]
+        v6 = rng.normal(0, sigma, 6)
+        cmd = np.clip(centre + rng.normal(0, 0.03, 6), 0, 1)
+        du, it = wls(v6, 0.0 - cmd, 1.0 - cmd, B, None, None, Wv6, np.ones(6), None)
+        vs.append(v6)
+        cmds.append(cmd)
+        its.append(it)
+        ok.append(du is not None)
+        dus.append(np.zeros(6) if du is None else np.array(du))
+    return dict(kat, rnd_v=np.array(vs), rnd_cmd=np.array(cmds), rnd_du=np.array(dus),
+                rnd_iter=np.array(its), rnd_ok=np.array(ok), rnd_B=B, rnd_Wv=Wv6)
+
+
+def quat_fixture():
+    from dronesim.utils import math as rm
+    rng = np.random.default_rng(3)
+    q1 = rng.normal(size=(64, 4))
+    q1 /= np.linalg.norm(q1, axis=1, keepdims=True)
+    q2 = rng.normal(size=(64, 4))
+    q2 /= np.linalg.norm(q2, axis=1, keepdims=True)
+    inv = np.array([rm.quat_inv_comp(a, b) for a, b in zip(q1, q2)])
+    comp = np.array([rm.quat_comp(a, b) for a, b in zip(q1, q2)])
+    wrap = np.array([rm.quat_wrap_shortest(e.copy()) for e in inv])
+    ang = rng.uniform(-12, 12, 64)
+    nang = np.array([rm.norm_ang(a) for a in ang])
+    return dict(q1=q1, q2=q2, inv_comp=inv, comp=comp, wrap=wrap, ang=ang, norm_ang=nang)
+
+
+def traj_fixture():
+    """examples/fly_INDI_TrajectoryTrack.py:127-160,178-186 with control_freq_hz = 96."""
+    from dronesim.utils.trajGen import trajGenerator
+    gates = np.vstack((np.array([[-3.0, 0, 2]]), np.array([0.5, 1, 5]), np.array([3, 0, 2])))
+    traj = trajGenerator(gates, max_vel=0.7, gamma=1e6)
+    ts = np.arange(0, traj.TS[-1], 1 / 96)
+    rows = []
+    for ti in ts:
+        s = traj.get_des_state(ti)
+        rows.append(np.concatenate([s.pos, s.vel, s.acc, [s.yaw]]))
+    return dict(TS=np.array(traj.TS), table=np.array(rows), gates=gates)
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "wls_cases.npz"), **wls_fixture())
+    np.savez_compressed(os.path.join(HERE, "quat_helpers.npz"), **quat_fixture())
+    np.savez_compressed(os.path.join(HERE, "traj_3gates.npz"), **traj_fixture())
+    np.savez_compressed(os.path.join(HERE, "hover_robobee.npz"), cmds=hover_fixture())
+    for i, name in enumerate(["robobee", "tello", "hexa_6DOF_simple"]):
+        n_u = 6 if "hexa" in name else 4
+        fx = controller_fixture(lambda: ref_shims.quad_controller(name), n_u, seed=100 + i)
+        np.savez_compressed(os.path.join(HERE, "ctrl_%s.npz" % name), **fx)
+    fx = controller_fixture(lambda: ref_shims.hexa_controller("hexa_6DOF"), 6, seed=200)
+    np.savez_compressed(os.path.join(HERE, "ctrl_hexa_6DOF.npz"), **fx)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

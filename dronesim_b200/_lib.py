@@ -1,0 +1,153 @@
+"""ctypes binding of ``libdronesim_b200.so`` (the C ABI declared in ``include/dronesim_b200.h``).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, importing this module
+raises, and every entry point returns an error status when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdronesim_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(_HERE, "..", "include")
+
+DS_MAX_ROTORS = 6
+DS_MAX_TYPES = 8
+DS_MAX_DRONES_PER_ENV = 32
+DS_OBS_STRIDE = 22
+DS_NUM_STATS = 16
+
+DS_OK, DS_ERR_INVALID, DS_ERR_CUDA, DS_ERR_STATE, DS_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+DS_INTEG_QUAT, DS_INTEG_RPY = 0, 1
+DS_FLAG_GROUND, DS_FLAG_DRAG, DS_FLAG_DOWNWASH, DS_FLAG_STATS = 1, 2, 4, 8
+DS_LAW_QUAD, DS_LAW_6DOF = 0, 1
+DS_DONE_GOAL, DS_DONE_FLOOR, DS_DONE_TIME = 1, 2, 4
+DS_ORDER_PHYSICS_THEN_CONTROL, DS_ORDER_CONTROL_THEN_PHYSICS = 0, 1
+
+_R = DS_MAX_ROTORS
+
+
+class ds_config(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("drones_per_env", C.c_int32), ("substeps", C.c_int32), ("integrator", C.c_int32),
+        ("flags", C.c_uint32), ("device", C.c_int32), ("sim_freq", C.c_float), ("gravity", C.c_float),
+        ("neighbourhood_radius", C.c_float), ("done_goal_enable", C.c_int32), ("goal", C.c_float * 3),
+        ("goal_radius", C.c_float), ("done_floor_enable", C.c_int32), ("z_min", C.c_float),
+        ("max_steps", C.c_int32), ("env_offset", C.c_int32),
+    ]
+
+
+class ds_type_params(C.Structure):
+    _fields_ = [
+        ("n_u", C.c_int32), ("n_v", C.c_int32), ("law", C.c_int32), ("reserved", C.c_int32),
+        ("mass", C.c_double), ("J", C.c_double * 9), ("r_com", C.c_double * 3), ("kf", C.c_double), ("km", C.c_double),
+        ("rotor_pos", (C.c_double * 3) * _R), ("rotor_axis", (C.c_double * 3) * _R),
+        ("torque_axis", (C.c_double * 3) * _R), ("rotor_spin", C.c_double * _R),
+        ("pwm2rpm_scale", C.c_double * _R), ("pwm2rpm_const", C.c_double * _R),
+        ("min_pwm", C.c_double * _R), ("max_pwm", C.c_double * _R),
+        ("gnd_eff_coeff", C.c_double), ("prop_radius", C.c_double), ("gnd_eff_h_clip", C.c_double),
+        ("drag_coeff", C.c_double * 3), ("dw_coeff", C.c_double * 3),
+        ("kp_pos", C.c_double), ("kd_pos", C.c_double), ("att_gain", C.c_double * 3), ("rate_gain", C.c_double * 3),
+        ("G1", (C.c_double * _R) * _R), ("alloc", (C.c_double * _R) * _R),
+        ("wls_wv", C.c_double * _R), ("wls_gamma", C.c_double), ("init_cmd", C.c_double), ("init_thrust", C.c_double),
+    ]
+
+
+class ds_targets(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("num_wp", C.c_int32), ("advance_wp", C.c_int32), ("reserved", C.c_int32),
+        ("pos_yaw", C.c_void_p), ("vel", C.c_void_p), ("acc", C.c_void_p), ("table", C.c_void_p), ("offset", C.c_void_p),
+    ]
+
+
+class ds_state_views(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("n_pad", C.c_int64),
+        ("pos_thrust", C.c_void_p), ("quat", C.c_void_p), ("vel_rpm", C.c_void_p), ("omega_wp", C.c_void_p),
+        ("lastvel_done", C.c_void_p), ("lastrates_err", C.c_void_p), ("cmd0123", C.c_void_p), ("cmd45", C.c_void_p),
+        ("slot_type", C.c_void_p), ("step_counter", C.c_int64),
+    ]
+
+
+# every symbol include/dronesim_b200.h declares: name -> (restype, argtypes)
+_H = C.c_void_p
+SYMBOLS = {
+    "ds_create": (C.c_int, [C.POINTER(ds_config), C.POINTER(_H)]),
+    "ds_destroy": (None, [_H]),
+    "ds_set_types": (C.c_int, [_H, C.POINTER(ds_type_params), C.c_int32, C.POINTER(C.c_uint8)]),
+    "ds_reset": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_step": (C.c_int, [_H, C.POINTER(ds_targets), C.c_int32, C.c_int32, C.c_void_p]),
+    "ds_physics_step": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "ds_control_step": (C.c_int, [_H, C.POINTER(ds_targets), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_control_from_state": (C.c_int, [_H, C.c_void_p, C.POINTER(ds_targets), C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "ds_rate_control_step": (C.c_int, [_H, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "ds_get_obs": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_views": (C.c_int, [_H, C.POINTER(ds_state_views)]),
+    "ds_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
+    "ds_stats_reset": (C.c_int, [_H, C.c_void_p]),
+    "ds_step_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                               C.c_void_p]),
+    "ds_strerror": (C.c_char_p, [C.c_int]),
+    "ds_last_cuda_error": (C.c_int, [_H]),
+    "ds_abi_version": (C.c_int, []),
+    "ds_launch_count": (C.c_int64, [_H]),
+}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile ``csrc/ds_api.cu`` (which includes every kernel header) for sm_100a, in-tree."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "dronesim_b200.h")]
+    if not force and os.path.isfile(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "ds_api.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libdronesim_b200.so")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "dronesim_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        if L.ds_abi_version() != 1:
+            raise RuntimeError("dronesim_b200: ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+class DsError(RuntimeError):
+    pass
+
+
+def check(status: int, handle=None):
+    if status != DS_OK:
+        msg = lib().ds_strerror(status).decode()
+        if status == DS_ERR_CUDA and handle is not None:
+            msg += " [cudaError %d]" % lib().ds_last_cuda_error(handle)
+        raise DsError("dronesim_b200: %s" % msg)

@@ -1,0 +1,315 @@
+"""``SwarmCore``: thin Python owner of one ``ds_handle`` (one GPU's shard of environments).
+
+PyTorch is used for plumbing only (device buffers for targets / actions / observations, the
+current CUDA stream, zero-copy views of the handle's resident state); every computation of the
+hot path happens in ``libdronesim_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .vehicles import LAW_6DOF, VehicleType, load_vehicle
+
+
+class _CudaView:
+    """Minimal ``__cuda_array_interface__`` carrier for a borrowed device pointer."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner  # keeps the handle alive while the view exists
+
+
+def type_params(vt: VehicleType, composite: bool) -> L.ds_type_params:
+    """Pack a ``VehicleType`` into the C table.  ``composite=False`` uses the mass / inertia the
+    reference's parser reads (first link, BaseAviary.py:2055-2069: the literal ``Physics.DYN``
+    numbers); ``composite=True`` the whole kinematic tree (what PyBullet simulates)."""
+    p = L.ds_type_params()
+    n_u, n_v = vt.INDI_ACTUATOR_NR, vt.INDI_OUTPUT_NR
+    p.n_u, p.n_v, p.law = n_u, n_v, vt.law
+    if composite:
+        mass, J, rc = vt.M_TOTAL, np.asarray(vt.J_TOTAL, float), np.asarray(vt.COM, float)
+    else:
+        mass, J, rc = vt.M, np.asarray(vt.J, float), np.zeros(3)
+    p.mass = float(mass)
+    for i in range(9):
+        p.J[i] = float(J.reshape(-1)[i])
+    for i in range(3):
+        p.r_com[i] = float(rc[i])
+        p.drag_coeff[i] = float(vt.DRAG_COEFF[i])
+        p.att_gain[i] = float(vt.att_gain[i])
+        p.rate_gain[i] = float(vt.rate_gain[i])
+    p.kf, p.km = float(vt.KF), float(vt.KM)
+    for i in range(n_u):
+        for k in range(3):
+            p.rotor_pos[i][k] = float(vt.rotor_pos[i][k])
+            p.rotor_axis[i][k] = float(vt.rotor_axis[i][k])
+            p.torque_axis[i][k] = float(vt.torque_axis[i][k])
+        p.rotor_spin[i] = float(vt.rotor_spin[i])
+        p.pwm2rpm_scale[i] = float(vt.PWM2RPM_SCALE[i])
+        p.pwm2rpm_const[i] = float(vt.PWM2RPM_CONST[i])
+        p.min_pwm[i] = float(vt.MIN_PWM[i])
+        p.max_pwm[i] = float(vt.MAX_PWM[i])
+    p.gnd_eff_coeff, p.prop_radius, p.gnd_eff_h_clip = float(vt.GND_EFF_COEFF), float(vt.PROP_RADIUS), float(vt.GND_EFF_H_CLIP)
+    p.dw_coeff[0], p.dw_coeff[1], p.dw_coeff[2] = float(vt.DW_COEFF_1), float(vt.DW_COEFF_2), float(vt.DW_COEFF_3)
+    p.kp_pos, p.kd_pos = float(vt.guidance_indi_pos_gain), float(vt.guidance_indi_speed_gain)
+    alloc = vt.wls_unconstrained() if vt.law == LAW_6DOF else vt.pinv_alloc()  # [n_u][n_v]
+    for i in range(n_v):
+        for j in range(n_u):
+            p.G1[i][j] = float(vt.G1[i][j])
+    for i in range(n_u):
+        for j in range(n_v):
+            p.alloc[i][j] = float(alloc[i, j])
+    for i in range(n_v):
+        p.wls_wv[i] = float(vt.WLS_WV[i]) if n_v == 6 else float([1000.0, 1000.0, 0.1, 10.0][i])
+    p.wls_gamma = float(vt.WLS_GAMMA)
+    # controller reset values: INDIControl.py:127-129 vs INDIControl_6DOF.py:232-234
+    p.init_cmd = 0.5 if vt.law == LAW_6DOF else 0.0
+    p.init_thrust = 0.3 if vt.law == LAW_6DOF else 0.0
+    return p
+
+
+class SwarmCore:
+    """``n_envs`` environments x ``len(slot_models)`` drones resident on one GPU."""
+
+    def __init__(self, slot_models: Sequence, n_envs: int, *, integrator: str = "quat", composite: Optional[bool] = None,
+                 ground: bool = False, drag: bool = False, downwash: bool = False, stats: bool = False,
+                 freq: float = 240.0, aggregate_phy_steps: int = 1, neighbourhood_radius: float = math.inf,
+                 gravity: float = 9.8, goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0,
+                 device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None):
+        lib = L.lib()
+        self.vehicle_types: List[VehicleType] = [m if isinstance(m, VehicleType) else load_vehicle(m, assets_dir)
+                                                 for m in slot_models]
+        self.D, self.E = len(self.vehicle_types), int(n_envs)
+        self.N = self.D * self.E
+        self.K = int(aggregate_phy_steps)
+        self.SIM_FREQ = float(freq)
+        self.integrator = integrator
+        if composite is None:
+            composite = integrator == "quat"
+        self.composite = composite
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        cfg = L.ds_config()
+        cfg.n_envs, cfg.drones_per_env, cfg.substeps = self.E, self.D, self.K
+        cfg.integrator = L.DS_INTEG_RPY if integrator == "rpy" else L.DS_INTEG_QUAT
+        cfg.flags = ((L.DS_FLAG_GROUND if ground else 0) | (L.DS_FLAG_DRAG if drag else 0)
+                     | (L.DS_FLAG_DOWNWASH if downwash else 0) | (L.DS_FLAG_STATS if stats else 0))
+        cfg.device, cfg.sim_freq, cfg.gravity = self.device_index, float(freq), float(gravity)
+        cfg.neighbourhood_radius = float(neighbourhood_radius)
+        if goal is not None:
+            cfg.done_goal_enable = 1
+            cfg.goal[0], cfg.goal[1], cfg.goal[2] = [float(x) for x in goal]
+        cfg.goal_radius = float(goal_radius)
+        if z_min is not None:
+            cfg.done_floor_enable, cfg.z_min = 1, float(z_min)
+        cfg.max_steps, cfg.env_offset = int(max_steps), int(env_offset)
+        self._h = C.c_void_p()
+        L.check(lib.ds_create(C.byref(cfg), C.byref(self._h)))
+        # distinct types, in order of first appearance
+        names, self.slot_type = [], []
+        for vt in self.vehicle_types:
+            if vt.name not in names:
+                names.append(vt.name)
+            self.slot_type.append(names.index(vt.name))
+        self.type_names = names
+        uniq = [next(v for v in self.vehicle_types if v.name == n) for n in names]
+        arr = (L.ds_type_params * len(uniq))(*[type_params(v, composite) for v in uniq])
+        st = (C.c_uint8 * self.D)(*self.slot_type)
+        L.check(lib.ds_set_types(self._h, arr, len(uniq), st), self._h)
+        self.n_u = [vt.INDI_ACTUATOR_NR for vt in self.vehicle_types]
+        self._views = None
+        self._keep = []  # device tensors referenced by in-flight target structs
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().ds_destroy(self._h)
+            self._h = C.c_void_p()
+            self._views = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _host_f32(a, shape):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(shape))
+        return a
+
+    def reset(self, pos0, rpy0=None, vel0=None, action0=None, wp0=None):
+        """BaseAviary.reset + INDIControl.reset for every vehicle.  Host arrays, [E, D, ...] or [N, ...]."""
+        N = self.N
+        pos0 = self._host_f32(pos0, (N, 3))
+        rpy0 = self._host_f32(rpy0, (N, 3))
+        vel0 = self._host_f32(vel0, (N, 3))
+        action0 = self._host_f32(action0, (N, 6))
+        wp = None if wp0 is None else np.ascontiguousarray(np.asarray(wp0, dtype=np.int32).reshape(N))
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        with torch.cuda.device(self.device):
+            L.check(L.lib().ds_reset(self._h, ptr(pos0), ptr(rpy0), ptr(vel0), ptr(action0), ptr(wp), self._stream()),
+                    self._h)
+
+    # ------------------------------------------------------------------ targets
+    def _dev4(self, a, name):
+        """[N,4] float32 contiguous device tensor (numpy / torch in, padded from [N,3] if needed)."""
+        if a is None:
+            return None
+        t = torch.as_tensor(a, dtype=torch.float32, device=self.device) if not (
+            isinstance(a, torch.Tensor) and a.dtype == torch.float32 and a.device == self.device) else a
+        t = t.reshape(self.N, -1)
+        if t.shape[1] == 3:
+            t = torch.nn.functional.pad(t, (0, 1))
+        if t.shape[1] != 4:
+            raise ValueError("%s must have 3 or 4 columns" % name)
+        return t.contiguous()
+
+    def targets_per_vehicle(self, pos_yaw, vel=None, acc=None) -> L.ds_targets:
+        """mode 0: ``pos_yaw`` [N,4] (x,y,z,yaw), optional ``vel`` / ``acc`` [N,3|4]."""
+        t = L.ds_targets()
+        p, v, a = self._dev4(pos_yaw, "pos_yaw"), self._dev4(vel, "vel"), self._dev4(acc, "acc")
+        t.mode = 0
+        t.pos_yaw = p.data_ptr()
+        t.vel = v.data_ptr() if v is not None else None
+        t.acc = a.data_ptr() if a is not None else None
+        t._keep = (p, v, a)
+        return t
+
+    def targets_table(self, table, offset=None, advance: bool = True) -> L.ds_targets:
+        """mode 1: ``table`` [num_wp, 10] = pos3, vel3, acc3, yaw (the layout of the reference examples'
+        TARGET_POS/VEL/ACC/RPYS rows), shared by all vehicles; per-vehicle counters live in the state."""
+        tab = np.asarray(table, dtype=np.float64)
+        rows = np.zeros((tab.shape[0], 12), dtype=np.float32)
+        rows[:, 0:3], rows[:, 3] = tab[:, 0:3], tab[:, 9]
+        rows[:, 4:7], rows[:, 8:11] = tab[:, 3:6], tab[:, 6:9]
+        d = torch.from_numpy(rows).to(self.device)
+        off = self._dev4(offset, "offset")
+        t = L.ds_targets()
+        t.mode, t.num_wp, t.advance_wp = 1, int(tab.shape[0]), 1 if advance else 0
+        t.table = d.data_ptr()
+        t.offset = off.data_ptr() if off is not None else None
+        t._keep = (d, off)
+        return t
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, targets: L.ds_targets, n_control_steps: int = 1, order: int = L.DS_ORDER_PHYSICS_THEN_CONTROL):
+        """The fused hot path: n x (K physics substeps + one INDI evaluation)."""
+        L.check(L.lib().ds_step(self._h, C.byref(targets), int(n_control_steps), int(order), self._stream()), self._h)
+
+    def physics_step(self, action: torch.Tensor):
+        """``BaseAviary.step`` with an external action, device tensor [N, 6] (PWM)."""
+        a = action.reshape(self.N, 6)
+        assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()
+        L.check(L.lib().ds_physics_step(self._h, C.c_void_p(a.data_ptr()), self._stream()), self._h)
+
+    def _outs(self, want_cmd=True, want_aux=True):
+        cmd = torch.empty((self.N, 6), dtype=torch.float32, device=self.device) if want_cmd else None
+        pe = torch.empty((self.N, 3), dtype=torch.float32, device=self.device) if want_aux else None
+        ye = torch.empty((self.N,), dtype=torch.float32, device=self.device) if want_aux else None
+        return cmd, pe, ye
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def control_step(self, targets, control_timestep: float):
+        cmd, pe, ye = self._outs()
+        L.check(L.lib().ds_control_step(self._h, C.byref(targets), C.c_float(control_timestep), self._p(cmd), self._p(pe),
+                                        self._p(ye), self._stream()), self._h)
+        return cmd, pe, ye
+
+    def control_from_state(self, state: torch.Tensor, targets, control_timestep: float):
+        s = state.reshape(self.N, L.DS_OBS_STRIDE)
+        assert s.is_cuda and s.dtype == torch.float32 and s.is_contiguous()
+        cmd, pe, ye = self._outs()
+        L.check(L.lib().ds_control_from_state(self._h, C.c_void_p(s.data_ptr()), C.byref(targets),
+                                              C.c_float(control_timestep), self._p(cmd), self._p(pe), self._p(ye),
+                                              self._stream()), self._h)
+        return cmd, pe, ye
+
+    def rate_control_step(self, rate_thrust: torch.Tensor, control_timestep: float):
+        r = rate_thrust.reshape(self.N, 4)
+        assert r.is_cuda and r.dtype == torch.float32 and r.is_contiguous()
+        cmd, _, _ = self._outs(True, False)
+        L.check(L.lib().ds_rate_control_step(self._h, C.c_void_p(r.data_ptr()), C.c_float(control_timestep), self._p(cmd),
+                                             self._stream()), self._h)
+        return cmd
+
+    def get_obs(self, state=True, neighbors=True, done=True, reward=False):
+        obs = torch.empty((self.N, L.DS_OBS_STRIDE), dtype=torch.float32, device=self.device) if state else None
+        nb = torch.empty((self.N,), dtype=torch.int32, device=self.device) if neighbors else None
+        dn = torch.empty((self.E,), dtype=torch.uint8, device=self.device) if done else None
+        rw = torch.empty((self.E,), dtype=torch.float32, device=self.device) if reward else None
+        L.check(L.lib().ds_get_obs(self._h, self._p(obs), self._p(nb), self._p(dn), self._p(rw), self._stream()), self._h)
+        return obs, nb, dn, rw
+
+    def step_host(self, host_pos_yaw: torch.Tensor, host_obs: Optional[torch.Tensor], host_done: Optional[torch.Tensor]):
+        """End-to-end control step with HOST (ideally pinned) buffers; synchronises."""
+        L.check(L.lib().ds_step_host(self._h, C.c_void_p(host_pos_yaw.data_ptr()),
+                                     self._p(host_obs), self._p(host_done), self._stream()), self._h)
+
+    # ------------------------------------------------------------------ state access
+    def views(self) -> dict:
+        """Zero-copy torch views of the resident state (valid until ``close``)."""
+        v = L.ds_state_views()
+        L.check(L.lib().ds_views(self._h, C.byref(v)), self._h)
+        npad, n = int(v.n_pad), int(v.n)
+
+        def f4(ptr, cols=4):
+            return torch.as_tensor(_CudaView(ptr, (npad, cols), "<f4", self), device=self.device)[:n]
+
+        pos_t, quat, vel_r, om_w = f4(v.pos_thrust), f4(v.quat), f4(v.vel_rpm), f4(v.omega_wp)
+        lv_d, lr_e, c0, c1 = f4(v.lastvel_done), f4(v.lastrates_err), f4(v.cmd0123), f4(v.cmd45, 2)
+        return {
+            "pos": pos_t[:, :3], "last_thrust": pos_t[:, 3], "quat": quat, "vel": vel_r[:, :3], "rpm_sum": vel_r[:, 3],
+            "omega_body": om_w[:, :3], "wp_counter": om_w.view(torch.int32)[:, 3], "last_vel": lv_d[:, :3],
+            "done_bits": lv_d.view(torch.int32)[:, 3], "last_rates": lr_e[:, :3], "pos_err": lr_e[:, 3],
+            "cmd0123": c0, "cmd45": c1, "step_counter": int(v.step_counter),
+        }
+
+    def cmd(self) -> torch.Tensor:
+        v = self.views()
+        return torch.cat([v["cmd0123"], v["cmd45"]], dim=1)
+
+    @property
+    def step_counter(self) -> int:
+        v = L.ds_state_views()
+        L.check(L.lib().ds_views(self._h, C.byref(v)), self._h)
+        return int(v.step_counter)
+
+    def stats(self) -> dict:
+        out = (C.c_double * L.DS_NUM_STATS)()
+        L.check(L.lib().ds_stats(self._h, out, L.DS_NUM_STATS, self._stream()), self._h)
+        keys = ["control_evals", "sum_pos_err_sq", "saturated_cmds", "wls_slow_path", "wls_non_converged", "non_finite",
+                "min_altitude", "done_vehicles"]
+        return {k: out[i] for i, k in enumerate(keys)}
+
+    def stats_reset(self):
+        L.check(L.lib().ds_stats_reset(self._h, self._stream()), self._h)
+
+    def debug_wls(self, type_id: int, v: torch.Tensor, cmd: torch.Tensor, force_slow: bool = False):
+        """Diagnostic: the WLS allocator alone on n problems -> (du [n,6], iterations [n])."""
+        v = v.to(self.device, torch.float32).contiguous()
+        cmd = cmd.to(self.device, torch.float32).contiguous()
+        n = v.shape[0]
+        du = torch.empty((n, 6), dtype=torch.float32, device=self.device)
+        it = torch.empty((n,), dtype=torch.int32, device=self.device)
+        L.check(L.lib().ds_debug_wls(self._h, int(type_id), self._p(v), self._p(cmd), self._p(du), self._p(it), n,
+                                     1 if force_slow else 0, self._stream()), self._h)
+        return du, it
+
+    def launch_count(self) -> int:
+        return int(L.lib().ds_launch_count(self._h))

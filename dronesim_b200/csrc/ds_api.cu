@@ -1,0 +1,523 @@
+// C ABI of the dronesim_b200 core (see include/dronesim_b200.h for the contract of each entry).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/dronesim_b200.h"
+#include "ds_kernels.cuh"
+
+struct ds_handle {
+  ds_config cfg;
+  int n = 0, n_pad = 0, tile_v = 0, n_tiles = 0;
+  int n_types = 0;
+  bool types_set = false, is_reset = false;
+  bool nu6 = false, has_rc = false;
+  bool first_action_pending = false;  // s_a holds the caller's initial action (fly_INDI.py:214)
+  bool act_valid = false;             // s_a holds the last clipped external action (facade path)
+  int sm_count = 0;
+  int last_cuda = 0;
+  int64_t step_counter = 0;
+  int64_t launches = 0;
+  // device state
+  float4 *s_pos = nullptr, *s_quat = nullptr, *s_vel = nullptr, *s_om = nullptr, *s_lv = nullptr, *s_lr = nullptr;
+  float4 *s_c0 = nullptr, *s_a0 = nullptr;
+  float2 *s_c1 = nullptr, *s_a1 = nullptr;
+  DsTypeDev* d_types = nullptr;
+  DsWlsDev* d_wls = nullptr;
+  uint8_t* d_slot_type = nullptr;
+  float *d_init_cmd = nullptr, *d_init_thrust = nullptr;
+  double* d_stats = nullptr;
+  // staging for ds_reset / ds_step_host
+  float* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  float4* d_host_tgt = nullptr;
+  float* d_obs = nullptr;
+  uint8_t* d_done_env = nullptr;
+  uint8_t slot_type[DS_MAX_DRONES_PER_ENV];
+};
+
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) {                      \
+      h->last_cuda = (int)e_;                     \
+      return DS_ERR_CUDA;                         \
+    }                                             \
+  } while (0)
+
+extern "C" const char* ds_strerror(int s) {
+  switch (s) {
+    case DS_OK: return "ok";
+    case DS_ERR_INVALID: return "invalid argument";
+    case DS_ERR_CUDA: return "CUDA error (no CPU fallback exists; see ds_last_cuda_error)";
+    case DS_ERR_STATE: return "call order: ds_set_types and ds_reset must precede stepping";
+    case DS_ERR_UNSUPPORTED: return "unsupported configuration";
+  }
+  return "unknown status";
+}
+extern "C" int ds_abi_version(void) { return DS_ABI_VERSION; }
+extern "C" int ds_last_cuda_error(ds_handle* h) { return h ? h->last_cuda : 0; }
+extern "C" int64_t ds_launch_count(ds_handle* h) { return h ? h->launches : 0; }
+
+static void free_all(ds_handle* h) {
+  void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
+                  h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
+                  h->d_host_tgt, h->d_obs, h->d_done_env};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+}
+
+extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
+  if (!cfg || !out) return DS_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->n_envs <= 0 || cfg->drones_per_env <= 0 || cfg->substeps <= 0 || cfg->sim_freq <= 0.f) return DS_ERR_INVALID;
+  if (cfg->drones_per_env > DS_MAX_DRONES_PER_ENV) return DS_ERR_UNSUPPORTED;
+  if (cfg->integrator != DS_INTEG_QUAT && cfg->integrator != DS_INTEG_RPY) return DS_ERR_INVALID;
+  if ((int64_t)cfg->n_envs * cfg->drones_per_env > (int64_t)1 << 30) return DS_ERR_UNSUPPORTED;
+  ds_handle* h = new (std::nothrow) ds_handle();
+  if (!h) return DS_ERR_INVALID;
+  h->cfg = *cfg;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    delete h;
+    return DS_ERR_CUDA;  // no CUDA device: there is deliberately no CPU path
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return DS_ERR_CUDA; }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  const int D = cfg->drones_per_env;
+  h->n = cfg->n_envs * D;
+  h->tile_v = (DS_TILE / D) * D;
+  h->n_tiles = (h->n + h->tile_v - 1) / h->tile_v;
+  h->n_pad = ((h->n + DS_TILE - 1) / DS_TILE) * DS_TILE;
+  const size_t np = (size_t)h->n_pad;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+  };
+  alloc((void**)&h->s_pos, np * 16); alloc((void**)&h->s_quat, np * 16); alloc((void**)&h->s_vel, np * 16);
+  alloc((void**)&h->s_om, np * 16);  alloc((void**)&h->s_lv, np * 16);   alloc((void**)&h->s_lr, np * 16);
+  alloc((void**)&h->s_c0, np * 16);  alloc((void**)&h->s_a0, np * 16);
+  alloc((void**)&h->s_c1, np * 8);   alloc((void**)&h->s_a1, np * 8);
+  alloc((void**)&h->d_types, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
+  alloc((void**)&h->d_wls, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
+  alloc((void**)&h->d_slot_type, DS_MAX_DRONES_PER_ENV);
+  alloc((void**)&h->d_init_cmd, sizeof(float) * DS_MAX_TYPES_DEV);
+  alloc((void**)&h->d_init_thrust, sizeof(float) * DS_MAX_TYPES_DEV);
+  alloc((void**)&h->d_stats, sizeof(double) * DS_NUM_STATS);
+  if (e != cudaSuccess) {
+    free_all(h);
+    delete h;
+    return DS_ERR_CUDA;
+  }
+  *out = h;
+  return DS_OK;
+}
+
+extern "C" void ds_destroy(ds_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  free_all(h);
+  delete h;
+}
+
+static void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static bool inv3(const double* m, double* o) {
+  double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  if (det == 0.0 || !isfinite(det)) return false;
+  double id = 1.0 / det;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return true;
+}
+
+extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n_types, const uint8_t* slot_type) {
+  if (!h || !types || !slot_type || n_types <= 0 || n_types > DS_MAX_TYPES) return DS_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<DsTypeDev> dev(DS_MAX_TYPES_DEV);
+  std::vector<DsWlsDev> wls(DS_MAX_TYPES_DEV);
+  std::vector<float> icmd(DS_MAX_TYPES_DEV, 0.f), ithr(DS_MAX_TYPES_DEV, 0.f);
+  memset(dev.data(), 0, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
+  memset(wls.data(), 0, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
+  h->nu6 = false;
+  h->has_rc = false;
+  for (int t = 0; t < n_types; ++t) {
+    const ds_type_params& p = types[t];
+    if (p.n_u < 1 || p.n_u > DS_MAX_ROTORS || p.n_v < 1 || p.n_v > DS_MAX_ROTORS) return DS_ERR_INVALID;
+    if (p.law != DS_LAW_QUAD && p.law != DS_LAW_6DOF) return DS_ERR_INVALID;
+    if (p.law == DS_LAW_6DOF && (p.n_u != 6 || p.n_v != 6)) return DS_ERR_UNSUPPORTED;
+    if (p.law == DS_LAW_QUAD && p.n_v != 4) return DS_ERR_UNSUPPORTED;
+    if (!(p.mass > 0.0) || !(p.kf > 0.0)) return DS_ERR_INVALID;
+    DsTypeDev& d = dev[t];
+    double Ji[9];
+    if (!inv3(p.J, Ji)) return DS_ERR_INVALID;
+    // DS_INTEG_RPY integrates the state the reference's _dynamics integrates: no CoM offset
+    const double rc[3] = {h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[0],
+                          h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[1],
+                          h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[2]};
+    for (int i = 0; i < 9; ++i) { d.J[i] = (float)p.J[i]; d.Jinv[i] = (float)Ji[i]; }
+    for (int i = 0; i < 3; ++i) d.rc[i] = (float)rc[i];
+    if (rc[0] != 0.0 || rc[1] != 0.0 || rc[2] != 0.0) h->has_rc = true;
+    d.inv_mass = (float)(1.0 / p.mass);
+    d.kf = (float)p.kf;
+    d.gnd_k = (float)(p.gnd_eff_coeff * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
+    d.gnd_clip = (float)p.gnd_eff_h_clip;
+    for (int i = 0; i < 3; ++i) d.drag_k[i] = (float)(p.drag_coeff[i] * (2.0 * M_PI / 60.0));
+    d.dw_k1 = (float)(p.dw_coeff[0] * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
+    d.dw_k2 = (float)p.dw_coeff[1];
+    d.dw_k3 = (float)p.dw_coeff[2];
+    d.kp = (float)p.kp_pos;
+    d.kd = (float)p.kd_pos;
+    for (int i = 0; i < 3; ++i) { d.att[i] = (float)p.att_gain[i]; d.rate[i] = (float)p.rate_gain[i]; }
+    d.n_u = p.n_u;
+    d.law = p.law;
+    double rpm0 = 0.0;
+    for (int i = 0; i < p.n_u; ++i) {
+      DsRotorDev& r = d.rotor[i];
+      double arm[3], rel[3] = {p.rotor_pos[i][0] - rc[0], p.rotor_pos[i][1] - rc[1], p.rotor_pos[i][2] - rc[2]};
+      cross3(rel, p.rotor_axis[i], arm);
+      const double kq = p.rotor_spin[i] * (p.km / p.kf);
+      r.ax = (float)p.rotor_axis[i][0]; r.ay = (float)p.rotor_axis[i][1]; r.az = (float)p.rotor_axis[i][2];
+      r.mx = (float)(arm[0] + kq * p.torque_axis[i][0]);
+      r.my = (float)(arm[1] + kq * p.torque_axis[i][1]);
+      r.mz = (float)(arm[2] + kq * p.torque_axis[i][2]);
+      r.gx = (float)arm[0]; r.gy = (float)arm[1]; r.gz = (float)arm[2];
+      r.rx = (float)p.rotor_pos[i][0]; r.ry = (float)p.rotor_pos[i][1]; r.rz = (float)p.rotor_pos[i][2];
+      r.scale = (float)p.pwm2rpm_scale[i]; r.cnst = (float)p.pwm2rpm_const[i];
+      r.pmin = (float)p.min_pwm[i]; r.pmax = (float)p.max_pwm[i];
+      rpm0 += p.pwm2rpm_const[i];
+      for (int j = 0; j < p.n_v; ++j) d.alloc[i * 6 + j] = (float)p.alloc[i][j];
+    }
+    d.rpm0_sum = (float)rpm0;
+    if (p.n_u > 4) h->nu6 = true;
+    DsWlsDev& w = wls[t];
+    w.n_u = p.n_u; w.n_v = p.n_v; w.gamma = p.wls_gamma;
+    for (int i = 0; i < p.n_v; ++i) {
+      w.Wv[i] = p.wls_wv[i];
+      for (int j = 0; j < p.n_u; ++j) w.B[i * 6 + j] = p.G1[i][j] / 0.05;  // INDIControl_6DOF.py:627
+    }
+    for (int i = 0; i < p.n_u; ++i) { w.pmin[i] = p.min_pwm[i]; w.pmax[i] = p.max_pwm[i]; }
+    icmd[t] = (float)p.init_cmd;
+    ithr[t] = (float)p.init_thrust;
+  }
+  for (int s = 0; s < h->cfg.drones_per_env; ++s) {
+    if (slot_type[s] >= n_types) return DS_ERR_INVALID;
+    h->slot_type[s] = slot_type[s];
+  }
+  h->n_types = n_types;
+  CK(cudaMemcpy(h->d_types, dev.data(), sizeof(DsTypeDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_wls, wls.data(), sizeof(DsWlsDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_slot_type, h->slot_type, h->cfg.drones_per_env, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_init_cmd, icmd.data(), sizeof(float) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_init_thrust, ithr.data(), sizeof(float) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
+  h->types_set = true;
+  h->is_reset = false;
+  return DS_OK;
+}
+
+static int grid_for(const ds_handle* h, int blocks_wanted, int per_sm) {
+  int cap = h->sm_count * per_sm;
+  return blocks_wanted < cap ? (blocks_wanted > 0 ? blocks_wanted : 1) : cap;
+}
+
+static int ensure_stage(ds_handle* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return DS_OK;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr;
+  h->stage_bytes = 0;
+  CK(cudaMalloc((void**)&h->d_stage, bytes));
+  h->stage_bytes = bytes;
+  return DS_OK;
+}
+
+extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, const float* vel0, const float* action0,
+                        const int32_t* wp0, void* stream) {
+  if (!h || !pos0) return DS_ERR_INVALID;
+  if (!h->types_set) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  // staging layout: pos0 | rpy0 | vel0 | action0 | wp0
+  const size_t total = n * (3 + 3 + 3 + 6 + 1) * sizeof(float);
+  int rc = ensure_stage(h, total);
+  if (rc != DS_OK) return rc;
+  float* d_pos = h->d_stage;
+  float* d_rpy = d_pos + 3 * n;
+  float* d_vel = d_rpy + 3 * n;
+  float* d_act = d_vel + 3 * n;
+  int32_t* d_wp = reinterpret_cast<int32_t*>(d_act + 6 * n);
+  CK(cudaMemcpyAsync(d_pos, pos0, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (rpy0) CK(cudaMemcpyAsync(d_rpy, rpy0, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (vel0) CK(cudaMemcpyAsync(d_vel, vel0, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (action0) CK(cudaMemcpyAsync(d_act, action0, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (wp0) CK(cudaMemcpyAsync(d_wp, wp0, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  DsResetArgs a;
+  a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv; a.s_lr = h->s_lr;
+  a.s_c0 = h->s_c0; a.s_a0 = h->s_a0; a.s_c1 = h->s_c1; a.s_a1 = h->s_a1;
+  a.pos0 = d_pos; a.rpy0 = rpy0 ? d_rpy : nullptr; a.vel0 = vel0 ? d_vel : nullptr;
+  a.action0 = action0 ? d_act : nullptr; a.wp0 = wp0 ? d_wp : nullptr;
+  a.slot_type = h->d_slot_type; a.types = h->d_types; a.init_cmd = h->d_init_cmd; a.init_thrust = h->d_init_thrust;
+  a.n = h->n; a.n_pad = h->n_pad; a.D = h->cfg.drones_per_env;
+  ds_reset_kernel<<<grid_for(h, (h->n_pad + 255) / 256, 8), 256, 0, st>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * DS_NUM_STATS, st));
+  {
+    double big = 1.0e300;
+    CK(cudaMemcpyAsync(h->d_stats + 6, &big, sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaStreamSynchronize(st));  // the host arrays may be freed by the caller after return
+  h->step_counter = 0;
+  h->first_action_pending = (action0 != nullptr);
+  h->act_valid = false;
+  h->is_reset = true;
+  return DS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static void base_args(const ds_handle* h, DsArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv; a.s_lr = h->s_lr;
+  a.s_c0 = h->s_c0; a.s_c1 = h->s_c1; a.s_a0 = h->s_a0; a.s_a1 = h->s_a1;
+  a.types = h->d_types; a.wls = h->d_wls; a.slot_type = h->d_slot_type; a.stats = h->d_stats;
+  a.n = h->n; a.D = h->cfg.drones_per_env; a.tile_v = h->tile_v; a.n_tiles = h->n_tiles;
+  a.K = h->cfg.substeps; a.n_types = h->n_types;
+  a.flags = (h->cfg.flags & 0xFu) | (h->has_rc ? DS_HAS_RC : 0u);
+  a.dt = 1.0f / h->cfg.sim_freq;
+  a.gravity = h->cfg.gravity;
+  a.goal_en = h->cfg.done_goal_enable; a.floor_en = h->cfg.done_floor_enable;
+  a.goal_x = h->cfg.goal[0]; a.goal_y = h->cfg.goal[1]; a.goal_z = h->cfg.goal[2]; a.goal_r = h->cfg.goal_radius;
+  a.z_min = h->cfg.z_min;
+}
+
+static int set_targets(DsArgs& a, const ds_targets* t) {
+  if (!t) return DS_ERR_INVALID;
+  a.tmode = t->mode;
+  if (t->mode == 0) {
+    if (!t->pos_yaw) return DS_ERR_INVALID;
+    a.t_pos = (const float4*)t->pos_yaw; a.t_vel = (const float4*)t->vel; a.t_acc = (const float4*)t->acc;
+  } else if (t->mode == 1) {
+    if (!t->table || t->num_wp <= 0) return DS_ERR_INVALID;
+    a.t_table = (const float4*)t->table; a.t_off = (const float4*)t->offset;
+    a.num_wp = t->num_wp; a.advance_wp = t->advance_wp;
+  } else {
+    return DS_ERR_INVALID;
+  }
+  return DS_OK;
+}
+
+template <int INTEG, bool DW, bool NU6, int MODE>
+static void launch_step2(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
+  const int grid = grid_for(h, a.n_tiles, 2);
+  if (32 % a.D == 0) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
+  else ds_step_kernel<INTEG, DW, NU6, false, MODE><<<grid, DS_TILE, 0, st>>>(a);
+}
+template <int MODE>
+static void launch_step(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
+  const bool dw = (a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1;
+  const bool rpy = h->cfg.integrator == DS_INTEG_RPY;
+  const bool nu6 = h->nu6;
+#define DS_CASE(I, W, N) launch_step2<I, W, N, MODE>(h, a, st)
+  if (!rpy) {
+    if (dw) { if (nu6) DS_CASE(0, true, true); else DS_CASE(0, true, false); }
+    else    { if (nu6) DS_CASE(0, false, true); else DS_CASE(0, false, false); }
+  } else {
+    if (dw) { if (nu6) DS_CASE(1, true, true); else DS_CASE(1, true, false); }
+    else    { if (nu6) DS_CASE(1, false, true); else DS_CASE(1, false, false); }
+  }
+#undef DS_CASE
+}
+
+static void time_flags(const ds_handle* h, DsArgs& a) {
+  a.time_hit = (h->cfg.max_steps > 0 && h->step_counter + h->cfg.substeps >= h->cfg.max_steps) ? 1 : 0;
+}
+
+extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_steps, int32_t order, void* stream) {
+  if (!h || n_control_steps < 0 || (order != 0 && order != 1)) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  DsArgs a;
+  base_args(h, a);
+  int rc = set_targets(a, tgt);
+  if (rc != DS_OK) return rc;
+  a.order = order;
+  a.ctrl_dt = (float)h->cfg.substeps / h->cfg.sim_freq;  // CTRL_EVERY_N_STEPS * env.TIMESTEP (fly_INDI.py:231)
+  a.inv_ctrl_dt = h->cfg.sim_freq / (float)h->cfg.substeps;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_control_steps; ++i) {
+    a.use_act = (h->first_action_pending && order == 0) ? 1 : 0;
+    a.store_act = 0;
+    time_flags(h, a);
+    launch_step<0>(h, a, st);
+    h->launches++;
+    h->first_action_pending = false;
+    h->act_valid = false;
+    h->step_counter += h->cfg.substeps;  // BaseAviary.py:554
+  }
+  CK(cudaGetLastError());
+  return DS_OK;
+}
+
+extern "C" int ds_physics_step(ds_handle* h, const float* action, void* stream) {
+  if (!h || !action) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  DsArgs a;
+  base_args(h, a);
+  a.ext_action = action;
+  a.store_act = 1;
+  time_flags(h, a);
+  launch_step<1>(h, a, (cudaStream_t)stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->first_action_pending = false;
+  h->act_valid = true;
+  h->step_counter += h->cfg.substeps;
+  return DS_OK;
+}
+
+static int control_common(ds_handle* h, const float* state, const ds_targets* tgt, const float* rate_thrust,
+                          float control_timestep, float* cmd_out, float* pos_e_out, float* yaw_err_out, void* stream) {
+  if (!h || !(control_timestep > 0.f)) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  DsArgs a;
+  base_args(h, a);
+  if (!rate_thrust) {
+    int rc = set_targets(a, tgt);
+    if (rc != DS_OK) return rc;
+  }
+  a.ext_state = state;
+  a.rate_thrust = (const float4*)rate_thrust;
+  a.ctrl_dt = control_timestep;
+  a.inv_ctrl_dt = 1.0f / control_timestep;
+  a.cmd_out = cmd_out; a.pos_e_out = pos_e_out; a.yaw_err_out = yaw_err_out;
+  const int grid = grid_for(h, (h->n + DS_TILE - 1) / DS_TILE, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rate_thrust) {
+    if (h->nu6) ds_control_kernel<true, 1><<<grid, DS_TILE, 0, st>>>(a);
+    else ds_control_kernel<false, 1><<<grid, DS_TILE, 0, st>>>(a);
+  } else {
+    if (h->nu6) ds_control_kernel<true, 0><<<grid, DS_TILE, 0, st>>>(a);
+    else ds_control_kernel<false, 0><<<grid, DS_TILE, 0, st>>>(a);
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+  return DS_OK;
+}
+
+extern "C" int ds_control_step(ds_handle* h, const ds_targets* tgt, float control_timestep, float* cmd_out,
+                               float* pos_e_out, float* yaw_err_out, void* stream) {
+  return control_common(h, nullptr, tgt, nullptr, control_timestep, cmd_out, pos_e_out, yaw_err_out, stream);
+}
+extern "C" int ds_control_from_state(ds_handle* h, const float* state, const ds_targets* tgt, float control_timestep,
+                                     float* cmd_out, float* pos_e_out, float* yaw_err_out, void* stream) {
+  if (!state) return DS_ERR_INVALID;
+  return control_common(h, state, tgt, nullptr, control_timestep, cmd_out, pos_e_out, yaw_err_out, stream);
+}
+extern "C" int ds_rate_control_step(ds_handle* h, const float* rate_thrust, float control_timestep, float* cmd_out,
+                                    void* stream) {
+  if (!rate_thrust) return DS_ERR_INVALID;
+  return control_common(h, nullptr, nullptr, rate_thrust, control_timestep, cmd_out, nullptr, nullptr, stream);
+}
+
+extern "C" int ds_get_obs(ds_handle* h, float* obs, uint32_t* neighbors, uint8_t* done_env, float* reward_env,
+                          void* stream) {
+  if (!h) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  DsObsArgs a;
+  a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv;
+  // obs tail = last_clipped_action (BaseAviary.py:787): the external action on the facade path, else the
+  // controller command (which is the action the next physics step applies)
+  a.s_c0 = h->act_valid ? h->s_a0 : h->s_c0;
+  a.s_c1 = h->act_valid ? h->s_a1 : h->s_c1;
+  a.slot_type = h->d_slot_type; a.types = h->d_types;
+  a.obs = obs; a.neighbors = neighbors; a.done_env = done_env; a.reward_env = reward_env;
+  a.n = h->n; a.D = h->cfg.drones_per_env; a.nu6 = h->nu6 ? 1 : 0;
+  a.radius = h->cfg.neighbourhood_radius;
+  ds_obs_kernel<<<grid_for(h, (h->n + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  return DS_OK;
+}
+
+extern "C" int ds_views(ds_handle* h, ds_state_views* out) {
+  if (!h || !out) return DS_ERR_INVALID;
+  out->n = h->n; out->n_pad = h->n_pad;
+  out->pos_thrust = (float*)h->s_pos; out->quat = (float*)h->s_quat; out->vel_rpm = (float*)h->s_vel;
+  out->omega_wp = (float*)h->s_om; out->lastvel_done = (float*)h->s_lv; out->lastrates_err = (float*)h->s_lr;
+  out->cmd0123 = (float*)h->s_c0; out->cmd45 = (float*)h->s_c1;
+  out->slot_type = h->d_slot_type;
+  out->step_counter = h->step_counter;
+  return DS_OK;
+}
+
+extern "C" int ds_stats(ds_handle* h, double* host_out, int32_t n, void* stream) {
+  if (!h || !host_out || n <= 0 || n > DS_NUM_STATS) return DS_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(host_out, h->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return DS_OK;
+}
+extern "C" int ds_stats_reset(ds_handle* h, void* stream) {
+  if (!h) return DS_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * DS_NUM_STATS, (cudaStream_t)stream));
+  double big = 1.0e300;
+  CK(cudaMemcpyAsync(h->d_stats + 6, &big, sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return DS_OK;
+}
+
+extern "C" int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host_obs, uint8_t* host_done_env,
+                            void* stream) {
+  if (!h || !host_pos_yaw) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  if (!h->d_host_tgt) CK(cudaMalloc((void**)&h->d_host_tgt, (size_t)h->n_pad * 16));
+  if (host_obs && !h->d_obs) CK(cudaMalloc((void**)&h->d_obs, n * DS_OBS_STRIDE * sizeof(float)));
+  if (host_done_env && !h->d_done_env) CK(cudaMalloc((void**)&h->d_done_env, (size_t)h->cfg.n_envs));
+  CK(cudaMemcpyAsync(h->d_host_tgt, host_pos_yaw, n * 16, cudaMemcpyHostToDevice, st));
+  ds_targets t;
+  memset(&t, 0, sizeof(t));
+  t.mode = 0;
+  t.pos_yaw = (const float*)h->d_host_tgt;
+  int rc = ds_step(h, &t, 1, DS_ORDER_PHYSICS_THEN_CONTROL, stream);
+  if (rc != DS_OK) return rc;
+  if (host_obs || host_done_env) {
+    rc = ds_get_obs(h, host_obs ? h->d_obs : nullptr, nullptr, host_done_env ? h->d_done_env : nullptr, nullptr, stream);
+    if (rc != DS_OK) return rc;
+    if (host_obs) CK(cudaMemcpyAsync(host_obs, h->d_obs, n * DS_OBS_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_done_env) CK(cudaMemcpyAsync(host_done_env, h->d_done_env, (size_t)h->cfg.n_envs, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return DS_OK;
+}
+
+extern "C" int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out,
+                            int32_t* iter_out, int32_t n, int32_t force_slow, void* stream) {
+  if (!h || !v || !cmd || !du_out || !iter_out || n <= 0) return DS_ERR_INVALID;
+  if (!h->types_set) return DS_ERR_STATE;
+  if (type_id < 0 || type_id >= h->n_types) return DS_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  ds_wls_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_types, h->d_wls, type_id, v, cmd, du_out, iter_out, n,
+                                                               force_slow);
+  h->launches++;
+  CK(cudaGetLastError());
+  return DS_OK;
+}

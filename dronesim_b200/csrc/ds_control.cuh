@@ -1,0 +1,170 @@
+// INDI control laws, one vehicle per thread, FP32 (FP64 only inside the WLS slow path).
+//
+// Restates dronesim/control/INDIControl.py:232-490 (quad / 4 virtual controls) and
+// dronesim/control/INDIControl_6DOF.py:341-634 (hexa / 6 virtual controls + WLS allocation).
+//
+// Algebraic shortcuts (results equal to the reference's within FP32 rounding):
+//  * pinv(G) (INDIControl.py:319-339).  With r1,r2,r3 the columns of the ZYX rotation matrix the
+//    reference's G is [-T r2 | T cos(roll) r1 | r3], so  G^-1 e = (-(r2.e)/T, (r1.e)/(T cos(roll)), r3.e):
+//    three dot products instead of a 3x3 SVD.  (np.linalg.pinv only differs from the inverse below
+//    a 1e-15 relative singular value, i.e. |cos(roll)| < 1e-15.)
+//  * pinv(G1/0.05) (INDIControl.py:459) and the first-iteration WLS matrix (wls_alloc.py:190-259)
+//    are per-type constants precomputed on the host in FP64 (DsTypeDev::alloc).
+#pragma once
+#include "ds_device.cuh"
+#include "ds_wls.cuh"
+
+struct CtrlState {   // kinematic state the controller sees
+  float px, py, pz;
+  float qx, qy, qz, qw;
+  float vx, vy, vz;
+  float wx, wy, wz;  // BODY rates (the reference rotates the world rates first, INDIControl.py:428-430)
+};
+struct CtrlTarget { float x, y, z, yaw, vx, vy, vz, ax, ay, az; };
+struct CtrlMem { float lvx, lvy, lvz, lrx, lry, lrz, lthrust; float cmd[6]; };
+struct CtrlOut { float pex, pey, pez, yaw_err; int wls_iter; int sat; };
+
+template <bool NU6>
+__device__ __forceinline__ void ds_allocate_quad(const DsTypeDev& tp, const float nu[4], CtrlMem& m, CtrlOut& o) {
+  constexpr int NU = NU6 ? 6 : 4;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    if (i < tp.n_u) {
+      const float* a = tp.alloc + i * 6;
+      float du = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3];  // INDIControl.py:459
+      float c = m.cmd[i] + du;                                              // :486
+      float cc = ds_clampf(c, tp.rotor[i].pmin, tp.rotor[i].pmax);          // :487
+      o.sat += (cc != c);
+      m.cmd[i] = cc;
+    }
+  }
+}
+
+// rate loop shared by both laws: returns nu[0..2] and updates last_rates (INDIControl.py:428-453)
+__device__ __forceinline__ void ds_rate_loop(const DsTypeDev& tp, const CtrlState& s, float inv_dt, float rsp_p,
+                                             float rsp_q, float rsp_r, CtrlMem& m, float nu[3]) {
+  float aax = (s.wx - m.lrx) * inv_dt, aay = (s.wy - m.lry) * inv_dt, aaz = (s.wz - m.lrz) * inv_dt;
+  m.lrx = s.wx; m.lry = s.wy; m.lrz = s.wz;
+  nu[0] = (rsp_p - s.wx) * tp.rate[0] - aax;
+  nu[1] = (rsp_q - s.wy) * tp.rate[1] - aay;
+  nu[2] = (rsp_r - s.wz) * tp.rate[2] - aaz;
+}
+
+template <bool NU6>
+__device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWlsDev* __restrict__ wls_tab, int type_id,
+                                                const CtrlState& s, const CtrlTarget& t, float inv_dt, CtrlMem& m,
+                                                CtrlOut& o, bool want_yaw_err) {
+  // ---- position loop (INDIControl.py:278-296 / INDIControl_6DOF.py:390-413)
+  o.pex = t.x - s.px; o.pey = t.y - s.py; o.pez = t.z - s.pz;
+  float asx = (o.pex * tp.kp + t.vx - s.vx) * tp.kd;
+  float asy = (o.pey * tp.kp + t.vy - s.vy) * tp.kd;
+  float asz = (o.pez * tp.kp + t.vz - s.vz) * tp.kd;
+  float cax = (s.vx - m.lvx) * inv_dt, cay = (s.vy - m.lvy) * inv_dt, caz = (s.vz - m.lvz) * inv_dt;
+  m.lvx = s.vx; m.lvy = s.vy; m.lvz = s.vz;
+  const bool six = (tp.law == 1);
+  float tax = six ? 0.f : t.ax, tay = six ? 0.f : t.ay, taz = six ? 0.f : t.az;  // 6DOF ignores target_acc (:410)
+  float aex = ds_clampf(asx + tax - cax, -6.f, 6.f);
+  float aey = ds_clampf(asy + tay - cay, -6.f, 6.f);
+  float aez = ds_clampf(asz + taz - caz, -6.f, 6.f);
+
+  // ---- attitude: Euler angles and the rotation matrix the reference's G is built from
+  const float x = s.qx, y = s.qy, z = s.qz, w = s.qw;
+  float d = x * x + y * y + z * z + w * w;
+  Mat3 R = ds_rot(x, y, z, w, 2.0f / d);
+  float sarg = -2.0f * (x * z - w * y);
+  const bool gimbal = (sarg <= -DS_GIMBAL) || (sarg >= DS_GIMBAL);
+  float A_r = 2.0f * (y * z + w * x), B_r = w * w - x * x - y * y + z * z;
+  float A_y = 2.0f * (x * y + w * z), B_y = w * w + x * x - y * y - z * z;
+  float cphi, cpsi, spsi;
+  Mat3 Re = R;  // rotation matrix of the extracted Euler angles (== R unless gimbal branch)
+  float phi = 0.f, theta = 0.f, psi = 0.f;
+  const bool need_angles = (!six) || want_yaw_err || gimbal;
+  if (need_angles) ds_euler(x, y, z, w, phi, theta, psi);
+  if (!gimbal) {
+    cphi = B_r * rsqrtf(A_r * A_r + B_r * B_r);
+    float ny = rsqrtf(A_y * A_y + B_y * B_y);
+    cpsi = B_y * ny; spsi = A_y * ny;
+  } else {  // roll = 0, pitch = +-pi/2: rebuild the matrix from the branch's angles
+    float sth, cth;
+    sincosf(theta, &sth, &cth);
+    sincosf(psi, &spsi, &cpsi);
+    cphi = 1.f;
+    Re.m00 = cth * cpsi; Re.m10 = cth * spsi; Re.m20 = -sth;
+    Re.m01 = -spsi;      Re.m11 = cpsi;       Re.m21 = 0.f;
+    Re.m02 = sth * cpsi; Re.m12 = sth * spsi; Re.m22 = cth;
+  }
+  // G^-1 accel_e
+  const float T = 9.81f;  // INDIControl.py:314 (quirk Q2)
+  float u0 = Re.m00 * aex + Re.m10 * aey + Re.m20 * aez;
+  float u1 = Re.m01 * aex + Re.m11 * aey + Re.m21 * aez;
+  float u2 = Re.m02 * aex + Re.m12 * aey + Re.m22 * aez;
+  float dT = u2;
+  float thrust = m.lthrust + dT;  // INDIControl.py:347 / INDIControl_6DOF.py:491
+  o.wls_iter = 0;
+
+  if (!six) {
+    float dphi = -u1 * (1.0f / T);
+    float dtheta = u0 / (T * cphi);
+    float yaw_inc = ds_norm_ang(t.yaw - psi);  // :341
+    float te_r = phi + dphi, te_p = theta + dtheta, te_y = psi + yaw_inc;
+    o.yaw_err = te_y - psi;  // :227
+    // ---- attitude loop (INDIControl.py:388-402)
+    float4 tq = ds_quat_from_euler(te_r, te_p, te_y);
+    float ew = w * tq.w + x * tq.x + y * tq.y + z * tq.z;  // utils/math.py:23-31
+    float ex = w * tq.x - x * tq.w - y * tq.z + z * tq.y;
+    float ey = w * tq.y + x * tq.z - y * tq.w - z * tq.x;
+    float ez = w * tq.z - x * tq.y + y * tq.x - z * tq.w;
+    if (ew < 0.f) { ex = -ex; ey = -ey; ez = -ez; }  // quat_wrap_shortest, in place (quirk Q1)
+    float nu[4];
+    ds_rate_loop(tp, s, inv_dt, tp.att[0] * ex, tp.att[1] * ey, tp.att[2] * ez, m, nu);
+    nu[3] = dT;  // thrust - last_thrust (:454); dT avoids the FP32 cancellation of (lt + dT) - lt
+    m.lthrust = thrust;
+    ds_allocate_quad<NU6>(tp, nu, m, o);
+  } else {
+    if constexpr (NU6) {
+      o.yaw_err = 0.f - psi;  // target_euler = 0 (:495)
+      // attitude error: conj(q) (x) identity = (-x,-y,-z,w), no shortest wrap (:540-545)
+      float e0 = -x, e1 = -y, e2 = -z;
+      float r0 = cpsi * e0 + spsi * e1;  // inv(R_psi) (:551-557)
+      float r1 = -spsi * e0 + cpsi * e1;
+      float nu[6];
+      ds_rate_loop(tp, s, inv_dt, tp.att[0] * r0, tp.att[1] * r1, tp.att[2] * e2, m, nu);
+      // accel_error_body = R^T accel_e (:589) - uses the quaternion's own matrix, not the Euler one
+      nu[3] = R.m00 * aex + R.m10 * aey + R.m20 * aez;
+      nu[4] = R.m01 * aex + R.m11 * aey + R.m21 * aez;
+      nu[5] = R.m02 * aex + R.m12 * aey + R.m22 * aez;
+      m.lthrust = thrust;  // :598
+      // ---- allocation: first WLS iteration in closed form, du = M nu
+      float du[6];
+      bool feasible = true;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float* a = tp.alloc + i * 6;
+        du[i] = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3] + a[4] * nu[4] + a[5] * nu[5];
+        float umin = tp.rotor[i].pmin - m.cmd[i], umax = tp.rotor[i].pmax - m.cmd[i];
+        feasible = feasible && !(du[i] >= umax + 1.0f || du[i] <= umin - 1.0f);  // wls_alloc.py:264
+      }
+      o.wls_iter = 1;
+      if (!feasible) {  // rare: run the active-set iterations in FP64
+        const DsWlsDev* P = wls_tab + type_id;
+        double v[6], umin[6], umax[6], u[6];
+        for (int i = 0; i < 6; ++i) {
+          v[i] = (double)nu[i];
+          umin[i] = P->pmin[i] - (double)m.cmd[i];
+          umax[i] = P->pmax[i] - (double)m.cmd[i];
+          u[i] = 0.0;
+        }
+        int it = ds_wls_alloc(P, v, umin, umax, u);
+        o.wls_iter = it;
+        for (int i = 0; i < 6; ++i) du[i] = (it > 0) ? (float)u[i] : 0.f;  // non-convergence: hold the command
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float c = m.cmd[i] + du[i];  // :630
+        float cc = ds_clampf(c, tp.rotor[i].pmin, tp.rotor[i].pmax);
+        o.sat += (cc != c);
+        m.cmd[i] = cc;
+      }
+    }
+  }
+}

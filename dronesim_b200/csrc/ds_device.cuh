@@ -1,0 +1,161 @@
+// Device-side data layout and math of the dronesim_b200 core (sm_100a).
+//
+// One thread advances one vehicle.  The resident state is a structure of float4 arrays so that a
+// warp moves 512 contiguous bytes per load/store instruction (LDG.128 / STG.128).  Per-type
+// airframe constants (rotor geometry, inertia, mixer / allocation matrix, gains) live in shared
+// memory, indexed by the lane's type id.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DS_TILE 256          // threads per CTA = vehicles per tile (when drones_per_env divides it)
+#define DS_MAX_TYPES_DEV 8
+
+struct __align__(16) DsRotorDev {
+  float ax, ay, az, scale;   // thrust axis (body)            | PWM2RPM_SCALE
+  float mx, my, mz, cnst;    // torque / unit thrust about CoM = (r - rc) x a + spin (km/kf) t | PWM2RPM_CONST
+  float gx, gy, gz, pmin;    // (r - rc) x a  (ground-effect thrust has no reaction torque) | MIN_PWM
+  float rx, ry, rz, pmax;    // rotor site in the base frame (ground-effect heights)        | MAX_PWM
+};
+
+struct __align__(16) DsTypeDev {
+  DsRotorDev rotor[6];       // 96 floats
+  float J[9];
+  float Jinv[9];
+  float rc[3];
+  float inv_mass;
+  float kf;
+  float gnd_k;               // GND_EFF_COEFF * (PROP_RADIUS/4)^2
+  float gnd_clip;            // GND_EFF_H_CLIP
+  float drag_k[3];           // DRAG_COEFF * 2 pi / 60
+  float dw_k1;               // DW_COEFF_1 * (PROP_RADIUS/4)^2
+  float dw_k2, dw_k3;
+  float kp, kd;
+  float att[3];
+  float rate[3];
+  float alloc[36];           // [n_u][6]
+  int n_u;
+  int law;
+  float rpm0_sum;            // sum_i PWM2RPM_CONST_i  (rpm of the all-zero action, BaseAviary.py:659-662)
+  float pad_[1];
+};
+static_assert(sizeof(DsTypeDev) % 16 == 0, "DsTypeDev must be float4-copyable");
+
+// FP64 side table for the WLS active-set slow path (rarely touched, stays in global / L2)
+struct DsWlsDev {
+  double B[36];    // [n_v][n_u] = G1 / 0.05, row stride 6
+  double Wv[6];
+  double gamma;
+  double pmin[6], pmax[6];
+  int n_u, n_v;
+};
+
+struct DsArgs {
+  // resident state (structure of float4 arrays)
+  float4* s_pos;   // x y z | last_thrust
+  float4* s_quat;  // x y z w
+  float4* s_vel;   // x y z | rpm sum of last applied action
+  float4* s_om;    // p q r | wp counter bits
+  float4* s_lv;    // last_vel | done bits
+  float4* s_lr;    // last_rates | |pos_e|
+  float4* s_c0;    // controller cmd 0..3
+  float2* s_c1;    // controller cmd 4..5
+  float4* s_a0;    // last clipped action 0..3 (facade path / first step after reset)
+  float2* s_a1;
+  const DsTypeDev* types;
+  const DsWlsDev* wls;
+  const uint8_t* slot_type;
+  double* stats;
+  int n;            // vehicles
+  int D;            // drones per env
+  int tile_v;       // vehicles per tile ( (DS_TILE / D) * D )
+  int n_tiles;
+  int K;
+  int n_types;
+  uint32_t flags;
+  int order;
+  int use_act;      // physics reads the action from s_a0/s_a1 instead of the controller cmd
+  int store_act;    // physics stores the clipped action to s_a0/s_a1
+  float dt;         // TIMESTEP
+  float gravity;
+  float ctrl_dt, inv_ctrl_dt;
+  // targets
+  int tmode, num_wp, advance_wp;
+  const float4* t_pos;
+  const float4* t_vel;
+  const float4* t_acc;
+  const float4* t_table;
+  const float4* t_off;
+  // done predicate
+  int goal_en, floor_en, time_hit;
+  float goal_x, goal_y, goal_z, goal_r;
+  float z_min;
+  // external I/O of the non-fused entry points
+  const float* ext_action;   // [n][6]
+  const float* ext_state;    // [n][22]
+  const float4* rate_thrust; // [n]
+  float* cmd_out;            // [n][6]
+  float* pos_e_out;          // [n][3]
+  float* yaw_err_out;        // [n]
+};
+
+// ---------------------------------------------------------------------------------------------
+// small math
+// ---------------------------------------------------------------------------------------------
+#define DS_PI_F 3.14159265358979323846f
+#define DS_GIMBAL 0.99999f
+
+__device__ __forceinline__ float ds_rcp(float x) { return __fdividef(1.0f, x); }
+
+struct Mat3 { float m00, m01, m02, m10, m11, m12, m20, m21, m22; };
+
+// btMatrix3x3::setRotation (oracle/pyb_math.py getMatrixFromQuaternion), s = 2/|q|^2
+__device__ __forceinline__ Mat3 ds_rot(float x, float y, float z, float w, float s) {
+  float xs = x * s, ys = y * s, zs = z * s;
+  float wx = w * xs, wy = w * ys, wz = w * zs;
+  float xx = x * xs, xy = x * ys, xz = x * zs;
+  float yy = y * ys, yz = y * zs, zz = z * zs;
+  Mat3 R;
+  R.m00 = 1.0f - (yy + zz); R.m01 = xy - wz;          R.m02 = xz + wy;
+  R.m10 = xy + wz;          R.m11 = 1.0f - (xx + zz); R.m12 = yz - wx;
+  R.m20 = xz - wy;          R.m21 = yz + wx;          R.m22 = 1.0f - (xx + yy);
+  return R;
+}
+
+// utils/math.py:75-80
+__device__ __forceinline__ float ds_norm_ang(float x) {
+  const float two_pi = 6.28318530717958647692f;
+  if (x > DS_PI_F) x -= two_pi * ceilf((x - DS_PI_F) / two_pi);
+  else if (x < -DS_PI_F) x += two_pi * ceilf((-DS_PI_F - x) / two_pi);
+  return x;
+}
+
+// pybullet getEulerFromQuaternion (oracle/pyb_math.py); returns gimbal flag
+__device__ __forceinline__ bool ds_euler(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
+  float sarg = -2.0f * (x * z - w * y);
+  if (sarg <= -DS_GIMBAL) { roll = 0.f; pitch = -0.5f * DS_PI_F; yaw = 2.0f * atan2f(x, -y); return true; }
+  if (sarg >= DS_GIMBAL)  { roll = 0.f; pitch = 0.5f * DS_PI_F;  yaw = 2.0f * atan2f(-x, y); return true; }
+  float sqx = x * x, sqy = y * y, sqz = z * z, squ = w * w;
+  roll = atan2f(2.0f * (y * z + w * x), squ - sqx - sqy + sqz);
+  pitch = asinf(sarg);
+  yaw = atan2f(2.0f * (x * y + w * z), squ + sqx - sqy - sqz);
+  return false;
+}
+
+// pybullet getQuaternionFromEuler
+__device__ __forceinline__ float4 ds_quat_from_euler(float r, float p, float y) {
+  float sph, cph, sth, cth, sps, cps;
+  sincosf(0.5f * r, &sph, &cph);
+  sincosf(0.5f * p, &sth, &cth);
+  sincosf(0.5f * y, &sps, &cps);
+  float4 q;
+  q.x = sph * cth * cps - cph * sth * sps;
+  q.y = cph * sth * cps + sph * cth * sps;
+  q.z = cph * cth * sps - sph * sth * cps;
+  q.w = cph * cth * cps + sph * sth * sps;
+  float n = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  q.x *= n; q.y *= n; q.z *= n; q.w *= n;
+  return q;
+}
+
+__device__ __forceinline__ float ds_clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }

@@ -1,0 +1,196 @@
+// Rigid-body dynamics + aerodynamic add-ons, K substeps in registers, one vehicle per thread.
+//
+// Restates (see oracle/dynamics.py for the FP64 twin and the list of repairs R1-R8):
+//   motor map + rotor thrust/torque  dronesim/envs/BaseAviary.py:1487-1543 (quad), :1398-1457 (hexa)
+//   _dynamics                        BaseAviary.py:1767-1828   (DS_INTEG_RPY)
+//   _groundEffect                    BaseAviary.py:1648-1699
+//   _drag                            BaseAviary.py:1705-1732
+//   _downwash                        BaseAviary.py:1736-1763
+// DS_INTEG_QUAT is Newton-Euler about the composite centre of mass with an exponential-map
+// quaternion update (asked by north_star; beyond the reference).
+//
+// The command is constant across the K substeps of a control step (BaseAviary.py:507-545), so the
+// rotor wrench sum_i T_i a_i, sum_i T_i m_i is hoisted out of the substep loop; only the terms
+// that depend on the moving state (ground effect, drag, downwash, gyroscopic torque) are per substep.
+#pragma once
+#include "ds_device.cuh"
+
+struct PhysState {
+  float px, py, pz;      // base-frame origin, world
+  float qx, qy, qz, qw;
+  float vx, vy, vz;      // velocity of the base-frame origin, world
+  float wx, wy, wz;      // body rates
+};
+
+#define DS_HAS_RC 0x100u  // internal flag: some type has a centre-of-mass offset
+
+__device__ __forceinline__ void ds_quat_step(float& qx, float& qy, float& qz, float& qw, float wx, float wy, float wz,
+                                             float dt) {
+  // q <- normalize(q (x) exp(w dt)); polynomial sin/cos of the half angle (|half| < 0.5), libm beyond
+  float tx = wx * dt, ty = wy * dt, tz = wz * dt;
+  float h2 = 0.25f * (tx * tx + ty * ty + tz * tz);  // (angle/2)^2
+  float k, c;
+  if (h2 < 0.25f) {
+    k = 0.5f * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f + h2 * (1.0f / 362880.0f)))));
+    c = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f + h2 * (-1.0f / 3628800.0f)))));
+  } else {
+    float half = sqrtf(h2), s;
+    sincosf(half, &s, &c);
+    k = 0.5f * s / half;
+  }
+  float dx = tx * k, dy = ty * k, dz = tz * k, dw = c;
+  float nx = qw * dx + qx * dw + qy * dz - qz * dy;
+  float ny = qw * dy - qx * dz + qy * dw + qz * dx;
+  float nz = qw * dz + qx * dy - qy * dx + qz * dw;
+  float nw = qw * dw - qx * dx - qy * dy - qz * dz;
+  float n = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+  qx = nx * n; qy = ny * n; qz = nz * n; qw = nw * n;
+}
+
+// act[] must already be clipped.  prev_rpm_sum: in = sum of rpm of the previously applied action
+// (BaseAviary.py:532), out = sum of rpm of this action.
+template <int INTEG, bool DW, bool NU6, bool WARPSYNC>
+__device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_tid0, float4* sh_pos,
+                                           const float* act, PhysState& s, float& prev_rpm_sum) {
+  constexpr int NU = NU6 ? 6 : 4;
+  const float dt = a.dt;
+  const bool gnd = (a.flags & 1u) != 0, drag = (a.flags & 2u) != 0;
+  const bool has_rc = (INTEG == 0) && ((a.flags & DS_HAS_RC) != 0);
+
+  // ---- per control step: rotor thrusts and the constant part of the body wrench
+  float Ti[NU];
+  float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    const DsRotorDev& r = tp.rotor[i];
+    float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
+    rpm_sum += rpm;
+    float T = tp.kf * rpm * rpm;                // :1515
+    Ti[i] = T;
+    F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
+    t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
+  }
+  const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
+
+  float roll = 0.f, pitch = 0.f, yaw = 0.f;
+  if (INTEG == 1) ds_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);  // state cache rpy (BaseAviary.py:729)
+
+  // QUAT: integrate centre-of-mass position / velocity
+  float cx = s.px, cy = s.py, cz = s.pz, ux = s.vx, uy = s.vy, uz = s.vz;
+  if (has_rc) {
+    Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+    cx += R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
+    cy += R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
+    cz += R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
+    float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
+    ux += R.m00 * kx + R.m01 * ky + R.m02 * kz;
+    uy += R.m10 * kx + R.m11 * ky + R.m12 * kz;
+    uz += R.m20 * kx + R.m21 * ky + R.m22 * kz;
+  }
+
+  for (int k = 0; k < a.K; ++k) {
+    Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+    float px = cx, py = cy, pz = cz, vx = ux, vy = uy, vz = uz;  // base-frame origin
+    if (has_rc) {
+      px -= R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
+      py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
+      pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
+    }
+    float Fx = F0x, Fy = F0y, Fz = F0z, tx = t0x, ty = t0y, tz = t0z;
+
+    if (gnd) {  // BaseAviary.py:1672-1699
+      bool gate;
+      if (INTEG == 1) gate = (fabsf(roll) < 0.5f * DS_PI_F) && (fabsf(pitch) < 0.5f * DS_PI_F);
+      else gate = (R.m22 > 0.f) && (fabsf(R.m20) < DS_GIMBAL);  // |roll| < pi/2 <=> cos(roll)cos(pitch) > 0
+      if (gate) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          const DsRotorDev& r = tp.rotor[i];
+          float h = pz + R.m20 * r.rx + R.m21 * r.ry + R.m22 * r.rz;
+          float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
+          float g = Ti[i] * tp.gnd_k * ih * ih;
+          Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
+          tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
+        }
+      }
+    }
+    if (drag) {  // BaseAviary.py:1719-1732, rpm of the previously applied action (:532,:545)
+      if (has_rc) {  // velocity of the base origin
+        float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
+        vx -= R.m00 * kx + R.m01 * ky + R.m02 * kz;
+        vy -= R.m10 * kx + R.m11 * ky + R.m12 * kz;
+        vz -= R.m20 * kx + R.m21 * ky + R.m22 * kz;
+      }
+      float sum = (k == 0) ? prev_rpm_sum : rpm_sum;
+      float d0 = -tp.drag_k[0] * sum * vx, d1 = -tp.drag_k[1] * sum * vy, d2 = -tp.drag_k[2] * sum * vz;
+      float fx = R.m00 * d0 + R.m01 * d1 + R.m02 * d2;
+      float fy = R.m10 * d0 + R.m11 * d1 + R.m12 * d2;
+      float fz = R.m20 * d0 + R.m21 * d1 + R.m22 * d2;
+      Fx += fx; Fy += fy; Fz += fz;
+      tx += -rcy * fz + rcz * fy; ty += -rcz * fx + rcx * fz; tz += -rcx * fy + rcy * fx;
+    }
+    if (DW) {  // BaseAviary.py:1747-1763: every drone of the env reads the same position snapshot
+      float4* buf = sh_pos + (k & 1) * DS_TILE;
+      buf[threadIdx.x] = make_float4(px, py, pz, 0.f);
+      if (WARPSYNC) __syncwarp(); else __syncthreads();
+      float fz = 0.f;
+      const float k1 = tp.dw_k1, k2 = tp.dw_k2, k3 = tp.dw_k3;
+      for (int j = 0; j < a.D; ++j) {
+        float4 o = buf[env_tid0 + j];
+        float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
+        float d2 = dx * dx + dy * dy;
+        float beta = fmaf(k2, dz, k3);
+        float dzc = fmaxf(dz, 1e-6f);
+        float t = ds_rcp(dzc * beta);  // 1 / (dz beta)
+        float idz = t * beta, ib = t * dzc;
+        float alpha = k1 * idz * idz;                          // DW1 (PROP_RADIUS / (4 dz))^2
+        float e = exp2f(-0.72134752044448170368f * d2 * ib * ib);  // exp(-0.5 (dxy / beta)^2)
+        bool on = (dz > 0.f) && (d2 < 100.f) && (beta != 0.f);
+        fz -= on ? alpha * e : 0.f;
+      }
+      Fz += fz;
+      tx += -rcy * fz; ty += rcx * fz;
+    }
+
+    // ---- Newton-Euler (BaseAviary.py:1790-1807)
+    float awx = (R.m00 * Fx + R.m01 * Fy + R.m02 * Fz) * tp.inv_mass;
+    float awy = (R.m10 * Fx + R.m11 * Fy + R.m12 * Fz) * tp.inv_mass;
+    float awz = (R.m20 * Fx + R.m21 * Fy + R.m22 * Fz) * tp.inv_mass - a.gravity;
+    const float* J = tp.J;
+    const float* Ji = tp.Jinv;
+    float jx = J[0] * s.wx + J[1] * s.wy + J[2] * s.wz;
+    float jy = J[3] * s.wx + J[4] * s.wy + J[5] * s.wz;
+    float jz = J[6] * s.wx + J[7] * s.wy + J[8] * s.wz;
+    float gx = tx - (s.wy * jz - s.wz * jy);
+    float gy = ty - (s.wz * jx - s.wx * jz);
+    float gz = tz - (s.wx * jy - s.wy * jx);
+    float wdx = Ji[0] * gx + Ji[1] * gy + Ji[2] * gz;
+    float wdy = Ji[3] * gx + Ji[4] * gy + Ji[5] * gz;
+    float wdz = Ji[6] * gx + Ji[7] * gy + Ji[8] * gz;
+    // ---- semi-implicit Euler (:1809-1812)
+    ux = fmaf(dt, awx, ux); uy = fmaf(dt, awy, uy); uz = fmaf(dt, awz, uz);
+    s.wx = fmaf(dt, wdx, s.wx); s.wy = fmaf(dt, wdy, s.wy); s.wz = fmaf(dt, wdz, s.wz);
+    cx = fmaf(dt, ux, cx); cy = fmaf(dt, uy, cy); cz = fmaf(dt, uz, cz);
+    if (INTEG == 1) {
+      roll = fmaf(dt, s.wx, roll); pitch = fmaf(dt, s.wy, pitch); yaw = fmaf(dt, s.wz, yaw);
+      float4 q = ds_quat_from_euler(roll, pitch, yaw);  // :1817
+      s.qx = q.x; s.qy = q.y; s.qz = q.z; s.qw = q.w;
+      ds_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);  // state refresh (:729)
+    } else {
+      ds_quat_step(s.qx, s.qy, s.qz, s.qw, s.wx, s.wy, s.wz, dt);
+    }
+  }
+  // back to base-frame origin
+  s.px = cx; s.py = cy; s.pz = cz; s.vx = ux; s.vy = uy; s.vz = uz;
+  if (has_rc) {
+    Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+    s.px -= R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
+    s.py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
+    s.pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
+    float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
+    s.vx -= R.m00 * kx + R.m01 * ky + R.m02 * kz;
+    s.vy -= R.m10 * kx + R.m11 * ky + R.m12 * kz;
+    s.vz -= R.m20 * kx + R.m21 * ky + R.m22 * kz;
+  }
+  prev_rpm_sum = rpm_sum;
+}

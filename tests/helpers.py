@@ -1,0 +1,36 @@
+"""Shared helpers for the parity tests: drive the CUDA core and the FP64 oracle side by side."""
+import numpy as np
+
+from oracle import pyb_math
+from oracle.sim import OracleSwarm
+
+
+def rpy_of_quat(q):
+    return np.array([pyb_math.getEulerFromQuaternion(x) for x in np.asarray(q, float).reshape(-1, 4)])
+
+
+def angle_between(q1, q2):
+    """Rotation angle (rad) between two xyzw unit quaternions, elementwise."""
+    q1 = np.asarray(q1, float).reshape(-1, 4)
+    q2 = np.asarray(q2, float).reshape(-1, 4)
+    d = np.abs(np.sum(q1 * q2, axis=1) / (np.linalg.norm(q1, axis=1) * np.linalg.norm(q2, axis=1)))
+    return 2.0 * np.arccos(np.clip(d, -1.0, 1.0))
+
+
+def make_pair(models, n_envs, integrator, K, gnd=False, drag=False, dw=False, radius=np.inf, **kw):
+    """(SwarmCore, OracleSwarm) with identical configuration."""
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.vehicles import load_vehicle
+
+    vts = [load_vehicle(m) for m in models]
+    composite = integrator == "quat"
+    core = SwarmCore(vts, n_envs, integrator=integrator, composite=composite, ground=gnd, drag=drag, downwash=dw,
+                     aggregate_phy_steps=K, neighbourhood_radius=radius, **kw)
+    orc = OracleSwarm(vts, n_envs, integrator=integrator, composite=composite, gnd=gnd, drag=drag, dw=dw,
+                      aggregate_phy_steps=K, neighbourhood_radius=radius)
+    return core, orc
+
+
+def core_state(core):
+    v = core.views()
+    return {k: (v[k].detach().cpu().numpy().astype(np.float64) if hasattr(v[k], "cpu") else v[k]) for k in v}

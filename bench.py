@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark: vehicle-steps/s of the fused dynamics + INDI hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (``config.workload``): BASELINE.json configs[4] "scaling sweep 1M-64M vehicles, fused 8
+substeps/control step" at 4 Mi vehicles PER GPU (262144 envs x 16 drones; weak scaling), each env
+being configs[3]'s heterogeneous swarm: 8 quads (robobee / tello) + 8 hexa_6DOF, ground effect +
+drag + downwash, K = 8 physics substeps per INDI evaluation, hover targets, noise off, quaternion
+integrator.  4 Mi vehicles = 461 MB of resident state per GPU, > 3.6x the 126 MB L2, so every step
+streams its state from HBM (no L2 flush needed between steps; said in ``config.l2``).
+
+One "step" = one control step = ONE launch of the fused kernel over the whole shard
+(K substeps + one INDI evaluation per vehicle) = N * K vehicle-steps.
+
+* ``value``      device-resident: targets already in HBM, CUDA events around exactly ``steps``
+                 launches, max over ranks.
+* ``e2e``        the same metric through the reference-facing C-ABI call with HOST buffers
+                 (``ds_step_host``): per step, pinned host targets [N][4] -> device, the fused
+                 step, per-env done flags -> pinned host memory, stream synchronised.
+* ``roofline``   algorithmic bytes (241 B per vehicle per control step) / launch
+                 duration against the measured HBM copy bandwidth; ``fp32`` is the second
+                 roofline the path is bounded by (FP32 instruction issue), measured live.
+* ``cpu_baseline`` the CPU oracle (per-vehicle FP64 Python restatement of the reference path,
+                 ``kind: port``) on all host cores, on a bounded sample of the same workload.
+
+``--impl reference`` times that CPU path alone (the reference has no runnable implementation of
+this path: its DYN code is dead and its controllers need PyBullet).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vehicle-steps/sec (dynamics+INDI ctrl)"
+UNIT = "vehicle-steps/s"
+K_SUBSTEPS = 8
+DRONES = 16
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--envs", type=int, default=262144, help="environments PER GPU (x16 drones)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 50)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_config(envs_per_gpu: int, n_gpus: int) -> dict:
+    return {
+        "workload": "hetero16 swarm (BASELINE configs[3]/[4]): %d envs x 16 drones = %d vehicles per GPU, "
+                    "8 quad (robobee/tello) + 8 hexa_6DOF per env, ground effect + drag + downwash, K=8 substeps "
+                    "fused per INDI control step, hover targets, quaternion integrator" % (envs_per_gpu, envs_per_gpu * DRONES),
+        "vehicles_per_gpu": envs_per_gpu * DRONES,
+        "vehicles_total": envs_per_gpu * DRONES * n_gpus,
+        "substeps_per_control_step": K_SUBSTEPS,
+        "sim_freq_hz": 240,
+        "parallelism": "envs sharded over %d GPU(s), no per-step collective" % n_gpus,
+        "l2": "inputs larger than L2 (resident state %.0f MB per GPU vs 126 MB L2); no flush" % (envs_per_gpu * DRONES * 110 / 1e6),
+    }
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples (NVML) taken DURING the timed regions."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._halt = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            while not self._halt.is_set():
+                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((clk, util))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report, do not fail the bench
+            self.error = repr(e)
+
+    def stop(self) -> dict:
+        self._halt.set()
+        self.join(timeout=2.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "error": self.error}
+        clk = sorted(c for c, _ in self.samples)
+        return {"sm_mhz": float(clk[len(clk) // 2]), "sm_max_mhz": float(self.sm_max) if self.sm_max else None,
+                "reasons": sorted(self.reasons), "samples": len(clk),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: the reference's own algorithm for this path on the host cores.
+
+    The reference's implementation of the path cannot run on the GPU box (or anywhere without
+    PyBullet; its explicit-dynamics code is dead), so this arm times the oracle
+    port: one process per core, each stepping whole hetero16 envs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.cpu_bench import time_oracle
+
+    cores = os.cpu_count() or 1
+    # bounded sample: one env (16 vehicles) per core per step is ~0.2 s of Python, so the driver's --steps/--warmup
+    # are honoured exactly up to 1000/100 steps (~4 min); beyond that they are clamped (and the line says so)
+    steps = max(1, min(args.steps, 1000))
+    warm = max(1, min(args.warmup, 100))
+    r = time_oracle(steps=steps, warmup=warm, workers=cores, envs_per_worker=1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.envs, args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU port of the reference path (oracle/), requested steps=%d warmup=%d clamped to %d/%d to bound the run; "
+                "the reference's own implementation of this path is not runnable (dead DYN code, PyBullet absent)"
+                % (args.steps, args.warmup, steps, warm),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dronesim_b200 import _lib as L
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.sharding import allreduce_stats
+    from dronesim_b200.workloads import hetero16, hetero16_bytes_per_control_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    E = args.envs
+    N = E * DRONES
+    models, K, flags, pos0, act0, tgt = hetero16(E, seed=0, env_offset=rank * E)
+    core = SwarmCore(models, E, integrator="quat", aggregate_phy_steps=K, stats=True, device=local_rank,
+                     env_offset=rank * E, **flags)
+    core.reset(pos0, action0=act0)
+    del pos0, act0
+    tgt32 = np.ascontiguousarray(tgt, dtype=np.float32)
+    d_tgt = torch.from_numpy(tgt32).to(dev)
+    d_vel = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+    d_acc = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+    targets = core.targets_per_vehicle(d_tgt, vel=d_vel, acc=d_acc)
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident timing -------------------------------------------------------------
+    core.step(targets, args.warmup)
+    barrier()
+    sampler.start()
+    l0 = core.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    core.step(targets, args.steps)
+    ev1.record()
+    barrier()
+    launches = core.launch_count() - l0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / args.steps
+    value = N * n_gpus * K * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 50)
+        h_tgt = torch.from_numpy(tgt32).pin_memory()
+        h_done = torch.zeros((E,), dtype=torch.uint8).pin_memory()
+        for _ in range(3):
+            core.step_host(h_tgt, None, h_done)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            core.step_host(h_tgt, None, h_done)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        e2e_s = max_over_ranks(t1 - t0)
+        e2e = {"value": N * n_gpus * K * e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_tgt.numel() * 4 * n_gpus), "d2h_bytes_per_step": int(h_done.numel() * n_gpus),
+               "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+               "call": "ds_step_host: pinned targets [N][4] f32 -> HBM, fused step, per-env done u8 -> pinned host, sync"}
+        # the gym-style variant that also returns every vehicle's 22-float state vector to the host
+        h_obs = torch.empty((N, L.DS_OBS_STRIDE), dtype=torch.float32).pin_memory()
+        core.step_host(h_tgt, h_obs, h_done)
+        barrier()
+        t0 = time.perf_counter()
+        n_obs = max(3, e2e_steps // 5)
+        for _ in range(n_obs):
+            core.step_host(h_tgt, h_obs, h_done)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        obs_s = max_over_ranks(t1 - t0)
+        e2e["with_full_obs"] = {"value": N * n_gpus * K * n_obs / obs_s, "unit": UNIT,
+                                "d2h_bytes_per_step": int((h_obs.numel() * 4 + h_done.numel()) * n_gpus), "steps": n_obs}
+        del h_obs
+    clocks = sampler.stop()
+
+    # ---- end-of-rollout statistics: the ONLY collective of the path --------------------------
+    stats = allreduce_stats(core.stats(), device=dev)
+    sane = (stats["non_finite"] == 0)
+
+    # ---- rooflines ---------------------------------------------------------------------------
+    peak, peak_src = hbm_peak()
+    bytes_per_launch = hetero16_bytes_per_control_step() * N
+    hbm_achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "ds_step_kernel<QUAT,DW,NU6,WARPSYNC,FUSED>",
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "algorithmic_bytes_per_vehicle_control_step": hetero16_bytes_per_control_step()}
+    prof = os.path.join(ROOT, "profiles", "roofline_inputs.json")
+    fp32 = None
+    if os.path.isfile(prof):  # ncu-derived per-launch constants (traffic, executed FP32 instructions), see DESIGN.md
+        try:
+            with open(prof) as f:
+                pin = json.load(f)
+            if pin.get("vehicles_per_launch"):
+                scale = N / float(pin["vehicles_per_launch"])
+                if pin.get("dram_bytes_per_launch"):
+                    roofline["traffic"] = pin["dram_bytes_per_launch"] * scale
+                if pin.get("fp32_flop_per_launch"):
+                    fl = pin["fp32_flop_per_launch"] * scale
+                    fp32 = {"flop_per_launch": fl, "source": pin.get("source", "profiles/")}
+        except Exception:
+            pass
+    if rank == 0:
+        import ctypes as C
+
+        pk = C.c_double(0.0)
+        if L.lib().ds_debug_fp32_peak(local_rank, C.byref(pk)) == 0 and pk.value > 0:
+            fp32 = fp32 or {}
+            fp32["peak_tflops_measured"] = pk.value
+            if "flop_per_launch" in fp32:
+                fp32["achieved_tflops"] = fp32["flop_per_launch"] / (ms_per_step * 1e-3) / 1e12
+                fp32["frac"] = fp32["achieved_tflops"] / pk.value
+    if fp32:
+        roofline["fp32"] = fp32
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_bench import time_oracle
+
+        r = time_oracle(steps=args.cpu_steps, warmup=1, workers=os.cpu_count() or 1, envs_per_worker=1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "seconds": r["seconds"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(E, n_gpus),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "control_steps_per_s": N * n_gpus * args.steps / (ms_total * 1e-3),
+            "rollout_stats": stats, "sane": bool(sane),
+        }
+        print(json.dumps(line), flush=True)
+    core.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if sane else 3
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -93,6 +93,7 @@ SYMBOLS = {
     "ds_step_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                C.c_void_p]),
+    "ds_debug_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "ds_strerror": (C.c_char_p, [C.c_int]),
     "ds_last_cuda_error": (C.c_int, [_H]),
     "ds_abi_version": (C.c_int, []),

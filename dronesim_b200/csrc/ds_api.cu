@@ -521,3 +521,50 @@ extern "C" int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const
   CK(cudaGetLastError());
   return DS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// FP32 roofline denominator: 8 independent FFMA chains per thread, all SMs, best of 5
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ds_fma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+        x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f) out[0] = s;  // never true for the arguments used; keeps the chains alive
+}
+
+extern "C" int ds_debug_fp32_peak(int32_t device, double* tflops_out) {
+  if (!tflops_out) return DS_ERR_INVALID;
+  int ndev = 0, sms = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DS_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return DS_ERR_CUDA;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, 4) != cudaSuccess) return DS_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 4096, blocks = sms * 2, threads = 1024;
+  double best = 0.0;
+  for (int r = 0; r < 6; ++r) {
+    cudaEventRecord(e0, 0);
+    ds_fma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return DS_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    if (r > 0 && ms > 0.f && flops / (ms * 1e-3) * 1e-12 > best) best = flops / (ms * 1e-3) * 1e-12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_out = best;
+  return DS_OK;
+}

@@ -1,0 +1,64 @@
+"""Synthetic swarms of the BASELINE.json configurations (SURVEY.md section 8 d), seeded numpy only.
+
+Shared by ``bench.py`` (both arms), the tests and ``__graft_entry__.smoke()`` so that the CUDA core
+and the CPU oracle always see the same inputs.  Nothing here touches the GPU.
+
+``hetero16`` is configs[3]/[4] of BASELINE.json: 16 drones per env, 8 quads (robobee / tello
+alternating) + 8 hexa_6DOF, slot -> type fixed per env, ground effect + drag + downwash, K = 8
+substeps per control step, hover at the initial position.
+
+Altitudes are distinct per slot (2.0 + 0.25 * slot): the reference's downwash model
+(BaseAviary.py:1753-1755) has alpha ~ 1 / dz^2, i.e. it is singular for two vehicles at (nearly)
+equal altitude - a 1e-16 m rounding difference between two "same altitude" vehicles produces a
+1e26 N force in the FP64 oracle.  SURVEY's "z = 1.0 + 0.25 (slot mod 4)" layout therefore cannot be
+flown by the reference formula at all; the layout below keeps every pair >= 0.25 m apart vertically.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+HETERO16_MODELS = ["robobee", "tello"] * 4 + ["hexa_6DOF"] * 8
+
+
+def hetero16(n_envs: int, seed: int = 0, env_offset: int = 0):
+    """(models, K, flags, pos0[E,16,3], action0[E,16,6], targets[E*16,4]) of the heterogeneous swarm.
+
+    The per-env random offsets are a pure function of (seed, global env index), so any sharding of
+    the envs over ranks reproduces the same swarm."""
+    D = 16
+    slot = np.arange(D)
+    base = np.stack([0.5 * (slot % 4), 0.5 * (slot // 4), 2.0 + 0.25 * slot], axis=1)  # [16,3]
+    # counter-based noise: hash of the global (env, slot, axis) index -> U(-0.02, 0.02)
+    e = (np.arange(n_envs, dtype=np.uint64) + np.uint64(env_offset))[:, None, None]
+    idx = (e * np.uint64(D) + slot.astype(np.uint64)[None, :, None]) * np.uint64(3) + np.arange(3, dtype=np.uint64)[None, None, :]
+    noise = (_hash01(idx, seed) - 0.5) * 0.04
+    pos0 = base[None, :, :] + noise
+    action0 = np.zeros((n_envs, D, 6))
+    action0[:, :8, :4] = 0.45
+    action0[:, 8:, :] = 0.45
+    tgt = np.concatenate([pos0.reshape(-1, 3), np.zeros((n_envs * D, 1))], axis=1)
+    flags = dict(ground=True, drag=True, downwash=True)
+    return HETERO16_MODELS, 8, flags, pos0, action0, tgt
+
+
+def _hash01(idx: np.ndarray, seed: int) -> np.ndarray:
+    """splitmix64 of (idx, seed) -> float64 in [0, 1)."""
+    with np.errstate(over="ignore"):
+        z = idx.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(seed + 1)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+# algorithmic bytes per vehicle per control step (SURVEY.md section 8 d, FP32 SoA, no padding)
+def algorithmic_bytes_per_control_step(n_u: int, per_vehicle_targets: bool = True) -> int:
+    phys = 2 * 4 * 13  # pos3 quat4 vel3 omega3, read + write
+    ctrl = 2 * 4 * (3 + 3 + 1 + n_u)  # last_vel3 last_rates3 last_thrust cmd[n_u], read + write
+    tgt = 4 * 10 if per_vehicle_targets else 8  # pos3 vel3 acc3 yaw | waypoint counter r+w
+    return phys + ctrl + tgt + 1  # + type id
+
+
+def hetero16_bytes_per_control_step() -> float:
+    """Mean over the 8 quads + 8 hexas of an env: (233 + 249) / 2 = 241 B."""
+    return 0.5 * (algorithmic_bytes_per_control_step(4) + algorithmic_bytes_per_control_step(6))

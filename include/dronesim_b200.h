@@ -205,6 +205,11 @@ int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host_obs, uint8
 int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out, int32_t* iter_out,
                  int32_t n, int32_t force_slow, void* stream);
 
+/* FP32 issue-rate micro-benchmark (bench bookkeeping: the FP32 roofline denominator, which
+ * MEASURED_PEAKS.json does not carry).  Runs 8 independent FFMA chains per thread on every SM of
+ * `device` and writes the best-of-5 rate in TFLOP/s (FMA = 2 FLOP) to *tflops_out (HOST). */
+int ds_debug_fp32_peak(int32_t device, double* tflops_out);
+
 /* ---- misc ------------------------------------------------------------------------------ */
 const char* ds_strerror(int status);
 int ds_last_cuda_error(ds_handle* h);

@@ -160,8 +160,13 @@ def test_cfg4_heterogeneous_downwash(models):
     core, orc = make_pair(models, E, "quat", K=8, gnd=True, drag=True, dw=True, radius=1.2)
     rng = np.random.default_rng(2)
     pos0 = np.zeros((E, D, 3))
-    for s in range(D):  # vertical stacks of two so that downwash is non-trivial
-        pos0[:, s] = [0.6 * (s // 2), 0.0, 1.0 + 0.8 * (s % 2)]
+    # vertical stacks of two so that downwash is non-trivial; columns 1.5 m apart because the reference's
+    # downwash model is singular for near-equal altitudes at small lateral distance (alpha ~ 1/dz^2), which
+    # makes any closed-loop comparison chaotic (the FP64 oracle itself diverges by 0.17 m for a 1e-7 m nudge
+    # at 0.6 m spacing).  Start at 2 m: the quad law restarts from cmd = 0 (INDIControl.py:129) and drops ~1.3 m
+    # before it recovers; crossing the ground-effect clip height makes the closed loop ill-conditioned as well.
+    for s in range(D):
+        pos0[:, s] = [1.5 * (s // 2), 0.0, 2.0 + 0.8 * (s % 2)]
     pos0 += rng.uniform(-0.02, 0.02, pos0.shape)
     act0 = np.zeros((E, D, 6))
     for s, m in enumerate(models):

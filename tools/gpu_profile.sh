@@ -1,0 +1,16 @@
+#!/bin/bash
+# ncu evidence for the bench command (run under gpurun, after the same command exited 0 without ncu).
+# Usage: bash tools/gpu_profile.sh <tag> [envs]
+set -u
+TAG=${1:-r1}
+ENVS=${2:-262144}
+CMD="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --envs ${ENVS}"
+mkdir -p gpurun_out
+$CMD > gpurun_out/plain_${TAG}.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/plain2_${TAG}.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:ds_step_kernel -s 10 -c 2 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
+echo "full capture rc=$?"
+tail -3 gpurun_out/ncu_full_${TAG}.log
+ls -la gpurun_out

@@ -16,7 +16,8 @@ struct ds_handle {
   int n = 0, n_pad = 0, tile_v = 0, n_tiles = 0;
   int n_types = 0;
   bool types_set = false, is_reset = false;
-  bool nu6 = false, has_rc = false;
+  bool nu6 = false;
+  bool map_identity = true;  // the tile map is the identity (one airframe class): warp-level downwash sync is legal
   bool first_action_pending = false;  // s_a holds the caller's initial action (fly_INDI.py:214)
   bool act_valid = false;             // s_a holds the last clipped external action (facade path)
   int sm_count = 0;
@@ -30,6 +31,7 @@ struct ds_handle {
   DsTypeDev* d_types = nullptr;
   DsWlsDev* d_wls = nullptr;
   uint8_t* d_slot_type = nullptr;
+  uint16_t* d_tile_map = nullptr;
   float *d_init_cmd = nullptr, *d_init_thrust = nullptr;
   double* d_stats = nullptr;
   // staging for ds_reset / ds_step_host
@@ -66,7 +68,7 @@ extern "C" int64_t ds_launch_count(ds_handle* h) { return h ? h->launches : 0; }
 
 static void free_all(ds_handle* h) {
   void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
-                  h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
+                  h->d_types, h->d_wls, h->d_slot_type, h->d_tile_map, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -107,6 +109,7 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   alloc((void**)&h->d_types, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_wls, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_slot_type, DS_MAX_DRONES_PER_ENV);
+  alloc((void**)&h->d_tile_map, sizeof(uint16_t) * DS_TILE);
   alloc((void**)&h->d_init_cmd, sizeof(float) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_init_thrust, sizeof(float) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_stats, sizeof(double) * DS_NUM_STATS);
@@ -152,7 +155,6 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
   memset(dev.data(), 0, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
   memset(wls.data(), 0, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
   h->nu6 = false;
-  h->has_rc = false;
   for (int t = 0; t < n_types; ++t) {
     const ds_type_params& p = types[t];
     if (p.n_u < 1 || p.n_u > DS_MAX_ROTORS || p.n_v < 1 || p.n_v > DS_MAX_ROTORS) return DS_ERR_INVALID;
@@ -169,15 +171,17 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
                           h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[2]};
     for (int i = 0; i < 9; ++i) { d.J[i] = (float)p.J[i]; d.Jinv[i] = (float)Ji[i]; }
     for (int i = 0; i < 3; ++i) d.rc[i] = (float)rc[i];
-    if (rc[0] != 0.0 || rc[1] != 0.0 || rc[2] != 0.0) h->has_rc = true;
+    d.has_rc = (rc[0] != 0.0 || rc[1] != 0.0 || rc[2] != 0.0) ? 1 : 0;
     d.inv_mass = (float)(1.0 / p.mass);
     d.kf = (float)p.kf;
     d.gnd_k = (float)(p.gnd_eff_coeff * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
     d.gnd_clip = (float)p.gnd_eff_h_clip;
     for (int i = 0; i < 3; ++i) d.drag_k[i] = (float)(p.drag_coeff[i] * (2.0 * M_PI / 60.0));
     d.dw_k1 = (float)(p.dw_coeff[0] * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
-    d.dw_k2 = (float)p.dw_coeff[1];
-    d.dw_k3 = (float)p.dw_coeff[2];
+    // exp(-0.5 (d / beta)^2) = exp2(-(d / beta')^2) with beta' = beta / sqrt(0.5 log2 e)
+    const double dw_s = sqrt(0.5 * 1.4426950408889634074);
+    d.dw_k2 = (float)(p.dw_coeff[1] / dw_s);
+    d.dw_k3 = (float)(p.dw_coeff[2] / dw_s);
     d.kp = (float)p.kp_pos;
     d.kd = (float)p.kd_pos;
     for (int i = 0; i < 3; ++i) { d.att[i] = (float)p.att_gain[i]; d.rate[i] = (float)p.rate_gain[i]; }
@@ -194,7 +198,7 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
       r.my = (float)(arm[1] + kq * p.torque_axis[i][1]);
       r.mz = (float)(arm[2] + kq * p.torque_axis[i][2]);
       r.gx = (float)arm[0]; r.gy = (float)arm[1]; r.gz = (float)arm[2];
-      r.rx = (float)p.rotor_pos[i][0]; r.ry = (float)p.rotor_pos[i][1]; r.rz = (float)p.rotor_pos[i][2];
+      r.rx = (float)rel[0]; r.ry = (float)rel[1]; r.rz = (float)rel[2];  // relative to the centre of mass
       r.scale = (float)p.pwm2rpm_scale[i]; r.cnst = (float)p.pwm2rpm_const[i];
       r.pmin = (float)p.min_pwm[i]; r.pmax = (float)p.max_pwm[i];
       rpm0 += p.pwm2rpm_const[i];
@@ -217,6 +221,29 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     h->slot_type[s] = slot_type[s];
   }
   h->n_types = n_types;
+  // ---- thread -> local vehicle map of a tile, sorted by airframe class (see ds_kernels.cuh)
+  {
+    const int D = h->cfg.drones_per_env, envs_per_tile = DS_TILE / D;
+    int cls[DS_MAX_DRONES_PER_ENV], n_cls = 0, keys[DS_MAX_DRONES_PER_ENV];
+    for (int s = 0; s < D; ++s) {
+      const DsTypeDev& d = dev[h->slot_type[s]];
+      const int key = d.law * 4 + (d.n_u > 4 ? 2 : 0) + d.has_rc;
+      int c = 0;
+      while (c < n_cls && keys[c] != key) ++c;
+      if (c == n_cls) keys[n_cls++] = key;
+      cls[s] = c;
+    }
+    uint16_t map[DS_TILE];
+    int t = 0;
+    for (int c = 0; c < n_cls; ++c)
+      for (int e = 0; e < envs_per_tile; ++e)
+        for (int s = 0; s < D; ++s)
+          if (cls[s] == c) map[t++] = (uint16_t)(e * D + s);
+    for (; t < DS_TILE; ++t) map[t] = 0xFFFF;
+    h->map_identity = true;
+    for (int i = 0; i < envs_per_tile * D; ++i) h->map_identity = h->map_identity && map[i] == i;
+    CK(cudaMemcpy(h->d_tile_map, map, sizeof(map), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(h->d_types, dev.data(), sizeof(DsTypeDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_wls, wls.data(), sizeof(DsWlsDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_slot_type, h->slot_type, h->cfg.drones_per_env, cudaMemcpyHostToDevice));
@@ -291,10 +318,10 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   memset(&a, 0, sizeof(a));
   a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv; a.s_lr = h->s_lr;
   a.s_c0 = h->s_c0; a.s_c1 = h->s_c1; a.s_a0 = h->s_a0; a.s_a1 = h->s_a1;
-  a.types = h->d_types; a.wls = h->d_wls; a.slot_type = h->d_slot_type; a.stats = h->d_stats;
+  a.types = h->d_types; a.wls = h->d_wls; a.slot_type = h->d_slot_type; a.tile_map = h->d_tile_map; a.stats = h->d_stats;
   a.n = h->n; a.D = h->cfg.drones_per_env; a.tile_v = h->tile_v; a.n_tiles = h->n_tiles;
   a.K = h->cfg.substeps; a.n_types = h->n_types;
-  a.flags = (h->cfg.flags & 0xFu) | (h->has_rc ? DS_HAS_RC : 0u);
+  a.flags = h->cfg.flags & 0xFu;
   a.dt = 1.0f / h->cfg.sim_freq;
   a.gravity = h->cfg.gravity;
   a.goal_en = h->cfg.done_goal_enable; a.floor_en = h->cfg.done_floor_enable;
@@ -321,7 +348,8 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
 template <int INTEG, bool DW, bool NU6, int MODE>
 static void launch_step2(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
   const int grid = grid_for(h, a.n_tiles, 2);
-  if (32 % a.D == 0) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
+  // warp-level sync of the downwash snapshot needs every env inside one warp: identity map and D | 32
+  if (32 % a.D == 0 && h->map_identity) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
   else ds_step_kernel<INTEG, DW, NU6, false, MODE><<<grid, DS_TILE, 0, st>>>(a);
 }
 template <int MODE>

@@ -10,12 +10,13 @@
 
 #define DS_TILE 256          // threads per CTA = vehicles per tile (when drones_per_env divides it)
 #define DS_MAX_TYPES_DEV 8
+#define DS_DW_ROWS 384       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2
 
 struct __align__(16) DsRotorDev {
   float ax, ay, az, scale;   // thrust axis (body)            | PWM2RPM_SCALE
   float mx, my, mz, cnst;    // torque / unit thrust about CoM = (r - rc) x a + spin (km/kf) t | PWM2RPM_CONST
   float gx, gy, gz, pmin;    // (r - rc) x a  (ground-effect thrust has no reaction torque) | MIN_PWM
-  float rx, ry, rz, pmax;    // rotor site in the base frame (ground-effect heights)        | MAX_PWM
+  float rx, ry, rz, pmax;    // rotor site relative to the centre of mass, r - rc (ground-effect heights) | MAX_PWM
 };
 
 struct __align__(16) DsTypeDev {
@@ -29,7 +30,7 @@ struct __align__(16) DsTypeDev {
   float gnd_clip;            // GND_EFF_H_CLIP
   float drag_k[3];           // DRAG_COEFF * 2 pi / 60
   float dw_k1;               // DW_COEFF_1 * (PROP_RADIUS/4)^2
-  float dw_k2, dw_k3;
+  float dw_k2, dw_k3;        // DW_COEFF_2,3 divided by sqrt(0.5 log2 e): exp(-0.5 (d/beta)^2) = exp2(-(d/beta')^2)
   float kp, kd;
   float att[3];
   float rate[3];
@@ -37,9 +38,11 @@ struct __align__(16) DsTypeDev {
   int n_u;
   int law;
   float rpm0_sum;            // sum_i PWM2RPM_CONST_i  (rpm of the all-zero action, BaseAviary.py:659-662)
-  float pad_[1];
+  int has_rc;                // centre of mass is not the base-frame origin (and the integrator is QUAT)
+  float pad_[24];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
 };
 static_assert(sizeof(DsTypeDev) % 16 == 0, "DsTypeDev must be float4-copyable");
+static_assert((sizeof(DsTypeDev) / 4) % 32 == 8, "DsTypeDev bank stride");
 
 // FP64 side table for the WLS active-set slow path (rarely touched, stays in global / L2)
 struct DsWlsDev {
@@ -65,6 +68,7 @@ struct DsArgs {
   const DsTypeDev* types;
   const DsWlsDev* wls;
   const uint8_t* slot_type;
+  const uint16_t* tile_map;  // [DS_TILE] thread -> vehicle index inside a tile (0xFFFF = idle); see ds_build_tile_map
   double* stats;
   int n;            // vehicles
   int D;            // drones per env
@@ -105,7 +109,10 @@ struct DsArgs {
 #define DS_PI_F 3.14159265358979323846f
 #define DS_GIMBAL 0.99999f
 
-__device__ __forceinline__ float ds_rcp(float x) { return __fdividef(1.0f, x); }
+// single-instruction MUFU forms (flush-to-zero, ~1 ulp): no denormal pre/post scaling around the SFU op
+__device__ __forceinline__ float ds_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ds_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ds_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 struct Mat3 { float m00, m01, m02, m10, m11, m12, m20, m21, m22; };
 

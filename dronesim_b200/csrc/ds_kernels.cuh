@@ -9,6 +9,13 @@
 //
 // Grid: persistent CTAs looping over tiles of tile_v vehicles (whole environments per tile, so the
 // downwash neighbour exchange never leaves the CTA); grid size = min(tiles, SMs x resident CTAs).
+//
+// Thread -> vehicle map.  Vehicles are env-major in memory (v = env * D + slot).  Inside a tile the
+// threads are re-ordered by airframe CLASS (control law, rotor count, centre-of-mass offset): thread t
+// handles local vehicle tile_map[t], where all slots of one class come first for every env of the tile,
+// then the next class.  With 8 quads + 8 hexas per env a warp is then 4 envs x 8 quads or 4 envs x 8
+// hexas: the control-law branch, the rotor loops (4 vs 6) and the centre-of-mass terms are warp-uniform,
+// while each group of 8 lanes still reads 128 contiguous bytes of every state array.
 #pragma once
 #include "ds_control.cuh"
 #include "ds_device.cuh"
@@ -79,24 +86,27 @@ template <int INTEG, bool DW, bool NU6, bool WARPSYNC, int MODE>
 __global__ void __launch_bounds__(DS_TILE, 2) ds_step_kernel(const DsArgs a) {
   __shared__ __align__(16) DsTypeDev sh_types[DS_MAX_TYPES_DEV];
   __shared__ uint8_t sh_slot_type[32];
-  __shared__ __align__(16) float4 sh_pos[DW ? 2 * DS_TILE : 1];
+  __shared__ __align__(16) float4 sh_pos[DW ? 2 * DS_DW_ROWS : 1];
   ds_load_types(a, sh_types);
   if (threadIdx.x < 32) sh_slot_type[threadIdx.x] = (threadIdx.x < a.D) ? a.slot_type[threadIdx.x] : 0;
   __syncthreads();
 
   constexpr int NU = NU6 ? 6 : 4;
   const int tid = threadIdx.x;
-  const int slot = tid % a.D;
-  const int env_tid0 = tid - slot;
+  const int lv_raw = a.tile_map[tid];
+  const bool lane_ok = lv_raw != 0xFFFF;
+  const int lv = lane_ok ? lv_raw : 0;  // idle lanes shadow local vehicle 0 (no stores) so barriers stay uniform
+  const int slot = lv % a.D;
+  const int env_row0 = (lv / a.D) * (a.D + DS_DW_PAD);  // padded row of the env's slot 0 in the downwash snapshot
+  const int my_row = env_row0 + slot;
   const int type_id = sh_slot_type[slot];
   const DsTypeDev& tp = sh_types[type_id];
-  const bool lane_ok = tid < a.tile_v;
   StatAcc st = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 3.0e38f, 0.f};
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int v = tile * a.tile_v + tid;
+    const int v = tile * a.tile_v + lv;
     const bool valid = lane_ok && v < a.n;
-    const int vv = valid ? v : 0;  // idle lanes shadow vehicle 0 (no stores) so barriers stay uniform
+    const int vv = valid ? v : 0;
 
     float4 P = a.s_pos[vv], Q = a.s_quat[vv], V = a.s_vel[vv], W = a.s_om[vv];
     PhysState s = {P.x, P.y, P.z, Q.x, Q.y, Q.z, Q.w, V.x, V.y, V.z, W.x, W.y, W.z};
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(DS_TILE, 2) ds_step_kernel(const DsArgs a) {
 #pragma unroll
       for (int i = 0; i < NU; ++i) act[i] = m.cmd[i];
     }
-    ds_physics<INTEG, DW, NU6, WARPSYNC>(a, tp, env_tid0, sh_pos, act, s, prev_rpm_sum);
+    ds_physics<INTEG, DW, NU6, WARPSYNC>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum);
     if (MODE == 0 && a.order == 0) control();
 
     // ---- done predicate on the fresh state (fly_INDI_TrajectoryTrack.py:249-250)

@@ -9,9 +9,16 @@
 // DS_INTEG_QUAT is Newton-Euler about the composite centre of mass with an exponential-map
 // quaternion update (asked by north_star; beyond the reference).
 //
-// The command is constant across the K substeps of a control step (BaseAviary.py:507-545), so the
-// rotor wrench sum_i T_i a_i, sum_i T_i m_i is hoisted out of the substep loop; only the terms
-// that depend on the moving state (ground effect, drag, downwash, gyroscopic torque) are per substep.
+// The kernel is bound by instruction issue (ncu: issue slots > 80 % busy, DRAM ~ 11 %), so the
+// code below is written to minimise issued instructions per substep:
+//  * the command is constant across the K substeps of a control step (BaseAviary.py:507-545), so
+//    the rotor wrench sum_i T_i a_i, sum_i T_i m_i is hoisted out of the substep loop; only the terms
+//    that depend on the moving state (ground effect, drag, downwash, gyroscopic torque) are per substep;
+//  * reciprocal / exp2 / rsqrt are the single-instruction MUFU forms (ds_rcp, ds_ex2, ds_rsqrt);
+//  * the downwash pair term is 19 instructions (see ds_downwash_pair): the Gaussian's 0.5 log2(e) is
+//    folded into the per-type beta coefficients, DW_COEFF_1 is applied once after the neighbour loop;
+//  * state is integrated in centre-of-mass coordinates; rotor sites are stored relative to the centre
+//    of mass so the ground-effect heights need no base-frame conversion.
 #pragma once
 #include "ds_device.cuh"
 
@@ -22,7 +29,7 @@ struct PhysState {
   float wx, wy, wz;      // body rates
 };
 
-#define DS_HAS_RC 0x100u  // internal flag: some type has a centre-of-mass offset
+#define DS_DW_PAD 1       // shared-memory position rows are padded to D + 1 float4: envs of a warp hit disjoint banks
 
 __device__ __forceinline__ void ds_quat_step(float& qx, float& qy, float& qz, float& qw, float wx, float wy, float wz,
                                              float dt) {
@@ -31,7 +38,7 @@ __device__ __forceinline__ void ds_quat_step(float& qx, float& qy, float& qz, fl
   float h2 = 0.25f * (tx * tx + ty * ty + tz * tz);  // (angle/2)^2
   float k, c;
   if (h2 < 0.25f) {
-    k = 0.5f * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f + h2 * (1.0f / 362880.0f)))));
+    k = 0.5f + h2 * (-0.5f / 6.0f + h2 * (0.5f / 120.0f + h2 * (-0.5f / 5040.0f + h2 * (0.5f / 362880.0f))));
     c = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f + h2 * (-1.0f / 3628800.0f)))));
   } else {
     float half = sqrtf(h2), s;
@@ -43,32 +50,71 @@ __device__ __forceinline__ void ds_quat_step(float& qx, float& qy, float& qz, fl
   float ny = qw * dy - qx * dz + qy * dw + qz * dx;
   float nz = qw * dz + qx * dy - qy * dx + qz * dw;
   float nw = qw * dw - qx * dx - qy * dy - qz * dz;
-  float n = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+  float n = ds_rsqrt(nx * nx + ny * ny + nz * nz + nw * nw);
   qx = nx * n; qy = ny * n; qz = nz * n; qw = nw * n;
+}
+
+// Downwash of every drone of the env on this one (BaseAviary.py:1747-1763), in units of DW_COEFF_1
+// (PROP_RADIUS / 4)^2: sum_j [dz > 0, dxy < 10] exp(-0.5 (dxy / beta)^2) / dz^2, beta = DW2 dz + DW3.
+// row: the env's position snapshot in shared memory; k2, k3 are pre-divided by sqrt(0.5 log2 e).
+// 19 issued instructions per pair: LDS.128, 3 FADD, FMUL+FFMA (dxy^2), FFMA (beta), FMUL+MUFU.RCP (1/dz^2),
+// MUFU.RCP (1/beta), 2 FMUL + MUFU.EX2 (Gaussian), FMUL, 2 FSETP (one predicate), predicated FADD.
+// dz > 0 also drops the drone itself.  beta == 0 (dz = -DW3 / DW2 exactly) gives 1/beta = inf -> exp2(-inf) = 0,
+// the reference's exp(-inf) (BaseAviary.py:1755), with no extra test.
+__device__ __forceinline__ void ds_downwash_pair(float& acc, const float4 o, float px, float py, float pz, float k2,
+                                                 float k3) {
+  const float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
+  const float d2 = fmaf(dy, dy, dx * dx);
+  const float ib = ds_rcp(fmaf(k2, dz, k3));   // 1 / beta'
+  const float idz2 = ds_rcp(dz * dz);          // 1 / dz^2
+  const float w = idz2 * ds_ex2((ib * ib) * -d2);
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f32 p, %1, 0f00000000;\n\t"
+      "setp.lt.and.f32 p, %2, 0f42C80000, p;\n\t"  // dxy^2 < 100
+      "@p add.f32 %0, %0, %3;\n\t}"
+      : "+f"(acc)
+      : "f"(dz), "f"(d2), "f"(w));
+}
+
+__device__ __forceinline__ float ds_downwash_sum(const float4* __restrict__ row, int D, float px, float py, float pz,
+                                                 float k2, float k3) {
+  float acc = 0.f;
+  if (D == 16) {  // BASELINE configs[3]/[4]
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ds_downwash_pair(acc, row[j], px, py, pz, k2, k3);
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < D; ++j) ds_downwash_pair(acc, row[j], px, py, pz, k2, k3);
+  }
+  return acc;
 }
 
 // act[] must already be clipped.  prev_rpm_sum: in = sum of rpm of the previously applied action
 // (BaseAviary.py:532), out = sum of rpm of this action.
 template <int INTEG, bool DW, bool NU6, bool WARPSYNC>
-__device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_tid0, float4* sh_pos,
+__device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_row0, int my_row, float4* sh_pos,
                                            const float* act, PhysState& s, float& prev_rpm_sum) {
   constexpr int NU = NU6 ? 6 : 4;
   const float dt = a.dt;
   const bool gnd = (a.flags & 1u) != 0, drag = (a.flags & 2u) != 0;
-  const bool has_rc = (INTEG == 0) && ((a.flags & DS_HAS_RC) != 0);
+  const bool has_rc = (INTEG == 0) && (tp.has_rc != 0);  // per type: warp-uniform when the tile map sorts by class
+  const int n_u = tp.n_u;
 
   // ---- per control step: rotor thrusts and the constant part of the body wrench
-  float Ti[NU];
+  float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
   float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
 #pragma unroll
   for (int i = 0; i < NU; ++i) {
-    const DsRotorDev& r = tp.rotor[i];
-    float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
-    rpm_sum += rpm;
-    float T = tp.kf * rpm * rpm;                // :1515
-    Ti[i] = T;
-    F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
-    t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
+    Tg[i] = 0.f;
+    if (i < n_u) {
+      const DsRotorDev& r = tp.rotor[i];
+      float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
+      rpm_sum += rpm;
+      float T = tp.kf * rpm * rpm;                // :1515
+      Tg[i] = T * tp.gnd_k;
+      F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
+      t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
+    }
   }
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
 
@@ -87,69 +133,60 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
     uy += R.m10 * kx + R.m11 * ky + R.m12 * kz;
     uz += R.m20 * kx + R.m21 * ky + R.m22 * kz;
   }
+  // drag coefficient x rotor speed sum: the first substep still sees the previously applied action (:532,:545)
+  const float dk0 = -tp.drag_k[0], dk1 = -tp.drag_k[1], dk2 = -tp.drag_k[2];
 
   for (int k = 0; k < a.K; ++k) {
-    Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    float px = cx, py = cy, pz = cz, vx = ux, vy = uy, vz = uz;  // base-frame origin
-    if (has_rc) {
-      px -= R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
-      py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
-      pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
-    }
+    const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
     float Fx = F0x, Fy = F0y, Fz = F0z, tx = t0x, ty = t0y, tz = t0z;
 
-    if (gnd) {  // BaseAviary.py:1672-1699
+    if (gnd) {  // BaseAviary.py:1672-1699; rotor sites are stored relative to the centre of mass
       bool gate;
       if (INTEG == 1) gate = (fabsf(roll) < 0.5f * DS_PI_F) && (fabsf(pitch) < 0.5f * DS_PI_F);
       else gate = (R.m22 > 0.f) && (fabsf(R.m20) < DS_GIMBAL);  // |roll| < pi/2 <=> cos(roll)cos(pitch) > 0
       if (gate) {
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          const DsRotorDev& r = tp.rotor[i];
-          float h = pz + R.m20 * r.rx + R.m21 * r.ry + R.m22 * r.rz;
-          float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
-          float g = Ti[i] * tp.gnd_k * ih * ih;
-          Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
-          tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
+          if (i < n_u) {
+            const DsRotorDev& r = tp.rotor[i];
+            float h = fmaf(R.m20, r.rx, fmaf(R.m21, r.ry, fmaf(R.m22, r.rz, cz)));
+            float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
+            float g = (Tg[i] * ih) * ih;
+            Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
+            tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
+          }
         }
       }
     }
-    if (drag) {  // BaseAviary.py:1719-1732, rpm of the previously applied action (:532,:545)
+    if (drag) {  // BaseAviary.py:1719-1732
+      float vx = ux, vy = uy, vz = uz;
       if (has_rc) {  // velocity of the base origin
         float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
         vx -= R.m00 * kx + R.m01 * ky + R.m02 * kz;
         vy -= R.m10 * kx + R.m11 * ky + R.m12 * kz;
         vz -= R.m20 * kx + R.m21 * ky + R.m22 * kz;
       }
-      float sum = (k == 0) ? prev_rpm_sum : rpm_sum;
-      float d0 = -tp.drag_k[0] * sum * vx, d1 = -tp.drag_k[1] * sum * vy, d2 = -tp.drag_k[2] * sum * vz;
+      const float sum = (k == 0) ? prev_rpm_sum : rpm_sum;
+      float d0 = (dk0 * sum) * vx, d1 = (dk1 * sum) * vy, d2 = (dk2 * sum) * vz;
       float fx = R.m00 * d0 + R.m01 * d1 + R.m02 * d2;
       float fy = R.m10 * d0 + R.m11 * d1 + R.m12 * d2;
       float fz = R.m20 * d0 + R.m21 * d1 + R.m22 * d2;
       Fx += fx; Fy += fy; Fz += fz;
-      tx += -rcy * fz + rcz * fy; ty += -rcz * fx + rcx * fz; tz += -rcx * fy + rcy * fx;
+      if (has_rc) { tx += -rcy * fz + rcz * fy; ty += -rcz * fx + rcx * fz; tz += -rcx * fy + rcy * fx; }
     }
     if (DW) {  // BaseAviary.py:1747-1763: every drone of the env reads the same position snapshot
-      float4* buf = sh_pos + (k & 1) * DS_TILE;
-      buf[threadIdx.x] = make_float4(px, py, pz, 0.f);
-      if (WARPSYNC) __syncwarp(); else __syncthreads();
-      float fz = 0.f;
-      const float k1 = tp.dw_k1, k2 = tp.dw_k2, k3 = tp.dw_k3;
-      for (int j = 0; j < a.D; ++j) {
-        float4 o = buf[env_tid0 + j];
-        float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
-        float d2 = dx * dx + dy * dy;
-        float beta = fmaf(k2, dz, k3);
-        float dzc = fmaxf(dz, 1e-6f);
-        float t = ds_rcp(dzc * beta);  // 1 / (dz beta)
-        float idz = t * beta, ib = t * dzc;
-        float alpha = k1 * idz * idz;                          // DW1 (PROP_RADIUS / (4 dz))^2
-        float e = exp2f(-0.72134752044448170368f * d2 * ib * ib);  // exp(-0.5 (dxy / beta)^2)
-        bool on = (dz > 0.f) && (d2 < 100.f) && (beta != 0.f);
-        fz -= on ? alpha * e : 0.f;
+      float px = cx, py = cy, pz = cz;  // base-frame origin
+      if (has_rc) {
+        px -= R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
+        py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
+        pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
       }
+      float4* buf = sh_pos + (k & 1) * DS_DW_ROWS;
+      buf[my_row] = make_float4(px, py, pz, 0.f);
+      if (WARPSYNC) __syncwarp(); else __syncthreads();
+      const float fz = -tp.dw_k1 * ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
       Fz += fz;
-      tx += -rcy * fz; ty += rcx * fz;
+      if (has_rc) { tx += -rcy * fz; ty += rcx * fz; }
     }
 
     // ---- Newton-Euler (BaseAviary.py:1790-1807)

@@ -7,11 +7,16 @@ and the CPU oracle always see the same inputs.  Nothing here touches the GPU.
 alternating) + 8 hexa_6DOF, slot -> type fixed per env, ground effect + drag + downwash, K = 8
 substeps per control step, hover at the initial position.
 
-Altitudes are distinct per slot (2.0 + 0.25 * slot): the reference's downwash model
-(BaseAviary.py:1753-1755) has alpha ~ 1 / dz^2, i.e. it is singular for two vehicles at (nearly)
-equal altitude - a 1e-16 m rounding difference between two "same altitude" vehicles produces a
-1e26 N force in the FP64 oracle.  SURVEY's "z = 1.0 + 0.25 (slot mod 4)" layout therefore cannot be
-flown by the reference formula at all; the layout below keeps every pair >= 0.25 m apart vertically.
+Layout: 4 x 4 lateral grid with 1.0 m pitch, altitude 2.0 + 0.25 * slot.  The reference's downwash
+model (BaseAviary.py:1753-1755) has alpha ~ 1 / dz^2, i.e. it is singular when a vehicle passes
+through the altitude of a laterally close neighbour: a 1e-16 m rounding difference between two
+"same altitude" vehicles 0.5 m apart produces a 1e26 N force in the FP64 oracle, and on the GPU a
+0.5 m grid lost ~0.1 % of 4 Mi vehicles to such crossings during the start-up transient (the quad
+law restarts from cmd = 0, INDIControl.py:129, and drops ~1.2 m before it recovers, robobee and
+tello by different amounts).  SURVEY's "0.5 m pitch, z = 1.0 + 0.25 (slot mod 4)" layout therefore
+cannot be flown by the reference formula at all.  At 1.0 m lateral pitch the Gaussian factor of a
+crossing pair is exp(-0.5 (1.0 / 0.11)^2) ~ 1e-18, which keeps the singularity harmless; the
+downwash arithmetic executed per pair is the same whatever the geometry (no early-out).
 """
 from __future__ import annotations
 
@@ -27,7 +32,7 @@ def hetero16(n_envs: int, seed: int = 0, env_offset: int = 0):
     the envs over ranks reproduces the same swarm."""
     D = 16
     slot = np.arange(D)
-    base = np.stack([0.5 * (slot % 4), 0.5 * (slot // 4), 2.0 + 0.25 * slot], axis=1)  # [16,3]
+    base = np.stack([1.0 * (slot % 4), 1.0 * (slot // 4), 2.0 + 0.25 * slot], axis=1)  # [16,3]
     # counter-based noise: hash of the global (env, slot, axis) index -> U(-0.02, 0.02)
     e = (np.arange(n_envs, dtype=np.uint64) + np.uint64(env_offset))[:, None, None]
     idx = (e * np.uint64(D) + slot.astype(np.uint64)[None, :, None]) * np.uint64(3) + np.arange(3, dtype=np.uint64)[None, None, :]

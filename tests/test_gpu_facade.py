@@ -1,0 +1,137 @@
+"""GPU: the drop-in facades (``dronesim_b200.envs.CtrlAviary``, ``dronesim_b200.control.INDIControl*``)
+driven exactly like the reference's example scripts, against the FP64 oracle running the same loop."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from dronesim_b200.vehicles import load_vehicle  # noqa: E402
+from helpers import angle_between  # noqa: E402
+from oracle.sim import OracleSwarm  # noqa: E402
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_fly_indi_loop_through_the_facades():
+    """examples/fly_INDI.py:139-262 with --physics dyn semantics: robobee, 240 Hz sim, 48 Hz control, 1 s."""
+    _need_gpu()
+    from dronesim_b200.control.INDIControl import INDIControl
+    from dronesim_b200.envs.CtrlAviary import CtrlAviary, Physics
+
+    SIM, CTRL = 240, 48
+    AGGR = int(SIM / CTRL)
+    INIT_XYZS = np.array([[0.0, 1.0, 0.5]])
+    env = CtrlAviary(drone_model=["robobee"], num_drones=1, initial_xyzs=INIT_XYZS, initial_rpys=np.zeros((1, 3)),
+                     physics=Physics.DYN, neighbourhood_radius=10, freq=SIM, aggregate_phy_steps=AGGR, gui=False)
+    assert env.AGGR_PHY_STEPS == 5 and env.TIMESTEP == 1 / 240 and env.NUM_DRONES == 1
+    assert env.drones[0].INDI_ACTUATOR_NR == 4 and env.drones[0].M == 0.75
+    ctrl = [INDIControl(drone_model="robobee")]
+    vt = load_vehicle("robobee")
+    orc = OracleSwarm([vt], 1, integrator="rpy", composite=False, aggregate_phy_steps=AGGR)
+    orc.reset(INIT_XYZS)
+    NUM_WP = CTRL * 15
+    TARGET_RPYS = np.array([[0, 0, 0.4 + i / 200] for i in range(NUM_WP)])
+    wp = 0
+    CTRL_EVERY_N_STEPS = int(np.floor(env.SIM_FREQ / CTRL))
+    action = {"0": np.array([0.4, 0.4, 0.4, 0.4])}
+    obs0 = env.reset()
+    assert set(obs0) == {"0"} and obs0["0"]["state"].shape == (20,) and obs0["0"]["neighbors"].shape == (1,)
+    act_o = np.zeros((1, 1, 6))
+    act_o[0, 0, :4] = 0.4
+    for i in range(0, 1 * SIM, AGGR):
+        obs, reward, done, info = env.step(action)
+        orc.physics_step(act_o)
+        assert reward == -1 and done is False and info == {"answer": 42}
+        if i % CTRL_EVERY_N_STEPS == 0:
+            action["0"], pos_e, yaw_e = ctrl[0].computeControlFromState(
+                control_timestep=CTRL_EVERY_N_STEPS * env.TIMESTEP, state=obs["0"]["state"], target_pos=np.array([0, 0, 0.5]),
+                target_rpy=TARGET_RPYS[wp])
+            act_o = orc.control_step(np.array([0, 0, 0.5]).reshape(1, 1, 3), tyaw=TARGET_RPYS[wp, 2].reshape(1, 1))
+            np.testing.assert_allclose(action["0"], act_o[0, 0, :4], atol=5e-5)
+            np.testing.assert_allclose(pos_e, orc.pos_e[0, 0], atol=1e-4)
+            wp = wp + 1 if wp < NUM_WP - 1 else 0
+    assert env.step_counter == orc.step_counter == 240
+    st = obs["0"]["state"]
+    ref = orc.state_vector(0, 0)
+    assert np.abs(st[0:3] - ref[0:3]).max() <= 1e-4
+    assert angle_between(st[3:7], ref[3:7]).max() <= 1e-4
+    np.testing.assert_allclose(st[7:10], ref[7:10], atol=1e-4)
+    np.testing.assert_allclose(st[16:20], ref[16:20], atol=5e-5)  # obs tail = last clipped action (PWM)
+    np.testing.assert_allclose(env.pos[0], ref[0:3], atol=1e-4)
+    np.testing.assert_allclose(ctrl[0].last_vel, orc.ctrl[0][0].last_vel, atol=1e-4)
+    env.close()
+    ctrl[0].close()
+
+
+def test_hetero_pair_hexa_and_quad_facade():
+    """A 6-rotor and a 4-rotor vehicle in one aviary (the reason the reference made actions dicts),
+    Physics.PYB_GND_DRAG_DW, each flown by its own controller class."""
+    _need_gpu()
+    from dronesim_b200.control.INDIControl import INDIControl
+    from dronesim_b200.control.INDIControl_6DOF import INDIControl as INDIControl6
+    from dronesim_b200.envs import CtrlAviary, Physics
+
+    models = ["hexa_6DOF", "tello"]
+    init = np.array([[0.0, 0.0, 1.0], [0.0, 0.1, 2.2]])
+    env = CtrlAviary(drone_model=models, num_drones=2, initial_xyzs=init, physics=Physics.PYB_GND_DRAG_DW, freq=240,
+                     aggregate_phy_steps=2, neighbourhood_radius=1.5)
+    ctrl = [INDIControl6(drone_model="hexa_6DOF"), INDIControl(drone_model="tello")]
+    with pytest.raises(ValueError):
+        INDIControl(drone_model="hexa_6DOF")  # 6 virtual controls need the 6-DOF class
+    vts = [load_vehicle(m) for m in models]
+    orc = OracleSwarm(vts, 1, integrator="quat", composite=True, gnd=True, drag=True, dw=True, aggregate_phy_steps=2,
+                      neighbourhood_radius=1.5)
+    orc.reset(init)
+    action = {"0": np.full(6, 0.1), "1": np.full(4, 0.4)}
+    act_o = np.zeros((1, 2, 6))
+    act_o[0, 0, :], act_o[0, 1, :4] = 0.1, 0.4
+    env.reset()
+    tpos = init.copy()
+    for i in range(48):
+        obs, _, _, _ = env.step(action)
+        orc.physics_step(act_o)
+        for j in range(2):
+            action[str(j)], _, _ = ctrl[j].computeControlFromState(control_timestep=2 / 240, state=obs[str(j)]["state"],
+                                                                   target_pos=tpos[j], target_rpy=np.zeros(3))
+        act_o = orc.control_step(tpos.reshape(1, 2, 3))
+        np.testing.assert_allclose(action["0"], act_o[0, 0, :6], atol=1e-4)
+        np.testing.assert_allclose(action["1"], act_o[0, 1, :4], atol=1e-4)
+    assert obs["0"]["state"].shape == (22,) and obs["1"]["state"].shape == (20,)
+    for j in range(2):
+        ref = orc.state_vector(0, j)
+        assert np.abs(obs[str(j)]["state"][0:3] - ref[0:3]).max() <= 1e-4
+        assert angle_between(obs[str(j)]["state"][3:7], ref[3:7]).max() <= 1e-4
+    adj = np.array([obs["0"]["neighbors"], obs["1"]["neighbors"]])
+    exp = orc.adjacency_bits()[0]
+    np.testing.assert_array_equal(adj, [[(exp[i] >> j) & 1 for j in range(2)] for i in range(2)])
+    env.close()
+    for c in ctrl:
+        c.close()
+
+
+def test_batched_facade_matches_single_env():
+    """num_envs > 1 returns device tensors; every env evolves exactly like the single-env facade."""
+    _need_gpu()
+    from dronesim_b200.envs import CtrlAviary, Physics
+
+    init = np.array([[0.0, 0.0, 1.0], [0.3, 0.0, 1.6]])
+    kw = dict(drone_model=["robobee", "tello"], num_drones=2, initial_xyzs=init, physics=Physics.PYB_DW, aggregate_phy_steps=4)
+    e1 = CtrlAviary(**kw)
+    e8 = CtrlAviary(num_envs=8, **kw)
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        a = {"0": 0.47 + rng.uniform(-0.05, 0.05, 4), "1": 0.49 + rng.uniform(-0.05, 0.05, 4)}
+        o1, r1, d1, _ = e1.step(a)
+        o8, r8, d8, _ = e8.step(a)
+    assert o8["state"].shape == (8, 2, 22) and o8["state"].is_cuda and r8.shape == (8,) and d8.shape == (8,)
+    s8 = o8["state"].cpu().numpy()
+    for e in range(8):
+        np.testing.assert_array_equal(s8[e, 0, :20], o1["0"]["state"].astype(np.float32))
+        np.testing.assert_array_equal(s8[e, 1, :20], o1["1"]["state"].astype(np.float32))
+    assert (r8.cpu().numpy() == -1).all() and not d8.cpu().numpy().any()
+    e1.close()
+    e8.close()

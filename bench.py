@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 50)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary (single-type) workloads")
     return ap.parse_args()
 
 
@@ -284,6 +285,44 @@ def run_ours(args):
     # ---- end-of-rollout statistics: the ONLY collective of the path --------------------------
     stats = allreduce_stats(core.stats(), device=dev)
     sane = (stats["non_finite"] == 0)
+    core.close()
+    del d_tgt, d_vel, d_acc, targets
+
+    # ---- secondary workloads: the single-type configs of BASELINE.json at the same vehicle count -------------
+    others = []
+    if not args.no_others:
+        from dronesim_b200.workloads import algorithmic_bytes_per_control_step, single_type
+
+        peak_o, _ = hbm_peak()
+        for name in ("quad_k8", "traj_quad", "hexa_circle"):
+            models_o, K_o, flags_o, p0, a0, tab, wp0 = single_type(name, N, seed=0, env_offset=rank * N)
+            c = SwarmCore(models_o, N, integrator="quat", aggregate_phy_steps=K_o, stats=True, device=local_rank, **flags_o)
+            c.reset(p0, action0=a0, wp0=wp0)
+            del p0, a0
+            tg = c.targets_table(tab)
+            steps_o = max(20, args.steps // 2)
+            c.step(tg, args.warmup)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c.step(tg, steps_o)
+            e1.record()
+            barrier()
+            ms_o = max_over_ranks(e0.elapsed_time(e1)) / steps_o
+            st_o = allreduce_stats(c.stats(), device=dev)
+            n_u = 6 if "hexa" in models_o[0] else 4
+            bytes_o = algorithmic_bytes_per_control_step(n_u, per_vehicle_targets=False)
+            gbs = bytes_o * N / (ms_o * 1e-3) / 1e9
+            others.append({"workload": name, "vehicles_per_gpu": N, "substeps_per_control_step": K_o, "flags": flags_o,
+                           "targets": "shared waypoint table + per-vehicle counter", "steps": steps_o, "ms_per_step": ms_o,
+                           "value": N * n_gpus * K_o / (ms_o * 1e-3), "unit": UNIT,
+                           "control_steps_per_s": N * n_gpus / (ms_o * 1e-3),
+                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_o, "unit": "GB/s", "frac": gbs / peak_o,
+                                        "algorithmic_bytes_per_vehicle_control_step": bytes_o},
+                           "sane": st_o["non_finite"] == 0})
+            sane = sane and st_o["non_finite"] == 0
+            c.close()
+            del tg
 
     # ---- rooflines ---------------------------------------------------------------------------
     peak, peak_src = hbm_peak()
@@ -337,10 +376,9 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(E, n_gpus),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "control_steps_per_s": N * n_gpus * args.steps / (ms_total * 1e-3),
-            "rollout_stats": stats, "sane": bool(sane),
+            "rollout_stats": stats, "sane": bool(sane), "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
-    core.close()
     if world > 1:
         dist.destroy_process_group()
     return 0 if sane else 3

@@ -11,7 +11,8 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdronesim_b200.so")
+# DRONESIM_B200_LIB selects an alternative build of the same ABI (kernel experiments: tools/build_variant.py)
+LIB_PATH = os.environ.get("DRONESIM_B200_LIB") or os.path.join(_HERE, "libdronesim_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_HERE, "..", "include")
 
@@ -104,20 +105,22 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC"]
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: str = None) -> str:
     """Compile ``csrc/ds_api.cu`` (which includes every kernel header) for sm_100a, in-tree."""
+    out_path = out_path or LIB_PATH
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "dronesim_b200.h")]
-    if not force and os.path.isfile(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
+    if not force and os.path.isfile(out_path) and all(os.path.getmtime(out_path) >= os.path.getmtime(s) for s in srcs):
+        return out_path
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "ds_api.cu")]
+    cmd = ([nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", out_path, os.path.join(CSRC, "ds_api.cu")])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libdronesim_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return out_path
 
 
 _lib = None

@@ -17,7 +17,6 @@ struct ds_handle {
   int n_types = 0;
   bool types_set = false, is_reset = false;
   bool nu6 = false;
-  bool map_identity = true;  // the tile map is the identity (one airframe class): warp-level downwash sync is legal
   bool first_action_pending = false;  // s_a holds the caller's initial action (fly_INDI.py:214)
   bool act_valid = false;             // s_a holds the last clipped external action (facade path)
   int sm_count = 0;
@@ -31,7 +30,6 @@ struct ds_handle {
   DsTypeDev* d_types = nullptr;
   DsWlsDev* d_wls = nullptr;
   uint8_t* d_slot_type = nullptr;
-  uint16_t* d_tile_map = nullptr;
   float *d_init_cmd = nullptr, *d_init_thrust = nullptr;
   double* d_stats = nullptr;
   // staging for ds_reset / ds_step_host
@@ -68,7 +66,7 @@ extern "C" int64_t ds_launch_count(ds_handle* h) { return h ? h->launches : 0; }
 
 static void free_all(ds_handle* h) {
   void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
-                  h->d_types, h->d_wls, h->d_slot_type, h->d_tile_map, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
+                  h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -109,7 +107,6 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   alloc((void**)&h->d_types, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_wls, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_slot_type, DS_MAX_DRONES_PER_ENV);
-  alloc((void**)&h->d_tile_map, sizeof(uint16_t) * DS_TILE);
   alloc((void**)&h->d_init_cmd, sizeof(float) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_init_thrust, sizeof(float) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_stats, sizeof(double) * DS_NUM_STATS);
@@ -221,29 +218,6 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     h->slot_type[s] = slot_type[s];
   }
   h->n_types = n_types;
-  // ---- thread -> local vehicle map of a tile, sorted by airframe class (see ds_kernels.cuh)
-  {
-    const int D = h->cfg.drones_per_env, envs_per_tile = DS_TILE / D;
-    int cls[DS_MAX_DRONES_PER_ENV], n_cls = 0, keys[DS_MAX_DRONES_PER_ENV];
-    for (int s = 0; s < D; ++s) {
-      const DsTypeDev& d = dev[h->slot_type[s]];
-      const int key = d.law * 4 + (d.n_u > 4 ? 2 : 0) + d.has_rc;
-      int c = 0;
-      while (c < n_cls && keys[c] != key) ++c;
-      if (c == n_cls) keys[n_cls++] = key;
-      cls[s] = c;
-    }
-    uint16_t map[DS_TILE];
-    int t = 0;
-    for (int c = 0; c < n_cls; ++c)
-      for (int e = 0; e < envs_per_tile; ++e)
-        for (int s = 0; s < D; ++s)
-          if (cls[s] == c) map[t++] = (uint16_t)(e * D + s);
-    for (; t < DS_TILE; ++t) map[t] = 0xFFFF;
-    h->map_identity = true;
-    for (int i = 0; i < envs_per_tile * D; ++i) h->map_identity = h->map_identity && map[i] == i;
-    CK(cudaMemcpy(h->d_tile_map, map, sizeof(map), cudaMemcpyHostToDevice));
-  }
   CK(cudaMemcpy(h->d_types, dev.data(), sizeof(DsTypeDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_wls, wls.data(), sizeof(DsWlsDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_slot_type, h->slot_type, h->cfg.drones_per_env, cudaMemcpyHostToDevice));
@@ -318,7 +292,7 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   memset(&a, 0, sizeof(a));
   a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv; a.s_lr = h->s_lr;
   a.s_c0 = h->s_c0; a.s_c1 = h->s_c1; a.s_a0 = h->s_a0; a.s_a1 = h->s_a1;
-  a.types = h->d_types; a.wls = h->d_wls; a.slot_type = h->d_slot_type; a.tile_map = h->d_tile_map; a.stats = h->d_stats;
+  a.types = h->d_types; a.wls = h->d_wls; a.slot_type = h->d_slot_type; a.stats = h->d_stats;
   a.n = h->n; a.D = h->cfg.drones_per_env; a.tile_v = h->tile_v; a.n_tiles = h->n_tiles;
   a.K = h->cfg.substeps; a.n_types = h->n_types;
   a.flags = h->cfg.flags & 0xFu;
@@ -347,9 +321,9 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
 
 template <int INTEG, bool DW, bool NU6, int MODE>
 static void launch_step2(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
-  const int grid = grid_for(h, a.n_tiles, 2);
-  // warp-level sync of the downwash snapshot needs every env inside one warp: identity map and D | 32
-  if (32 % a.D == 0 && h->map_identity) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
+  const int grid = grid_for(h, a.n_tiles, DS_MIN_CTAS);
+  // warp-level sync of the downwash snapshot needs every env inside one warp: D | 32
+  if (32 % a.D == 0) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
   else ds_step_kernel<INTEG, DW, NU6, false, MODE><<<grid, DS_TILE, 0, st>>>(a);
 }
 template <int MODE>

@@ -8,9 +8,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef DS_TILE
 #define DS_TILE 256          // threads per CTA = vehicles per tile (when drones_per_env divides it)
+#endif
+#ifndef DS_MIN_CTAS
+#define DS_MIN_CTAS 2        // resident CTAs per SM the step kernel is compiled for (register budget)
+#endif
 #define DS_MAX_TYPES_DEV 8
-#define DS_DW_ROWS 384       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2
+#define DS_DW_ROWS (DS_TILE + DS_TILE / 2)       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2
 
 struct __align__(16) DsRotorDev {
   float ax, ay, az, scale;   // thrust axis (body)            | PWM2RPM_SCALE
@@ -68,7 +73,6 @@ struct DsArgs {
   const DsTypeDev* types;
   const DsWlsDev* wls;
   const uint8_t* slot_type;
-  const uint16_t* tile_map;  // [DS_TILE] thread -> vehicle index inside a tile (0xFFFF = idle); see ds_build_tile_map
   double* stats;
   int n;            // vehicles
   int D;            // drones per env

@@ -10,12 +10,12 @@
 // Grid: persistent CTAs looping over tiles of tile_v vehicles (whole environments per tile, so the
 // downwash neighbour exchange never leaves the CTA); grid size = min(tiles, SMs x resident CTAs).
 //
-// Thread -> vehicle map.  Vehicles are env-major in memory (v = env * D + slot).  Inside a tile the
-// threads are re-ordered by airframe CLASS (control law, rotor count, centre-of-mass offset): thread t
-// handles local vehicle tile_map[t], where all slots of one class come first for every env of the tile,
-// then the next class.  With 8 quads + 8 hexas per env a warp is then 4 envs x 8 quads or 4 envs x 8
-// hexas: the control-law branch, the rotor loops (4 vs 6) and the centre-of-mass terms are warp-uniform,
-// while each group of 8 lanes still reads 128 contiguous bytes of every state array.
+// Thread -> vehicle map: vehicles are env-major in memory (v = env * D + slot) and thread t of a tile
+// handles local vehicle t, so a warp reads 512 contiguous bytes of every state array and (for D | 32)
+// holds whole envs: the downwash snapshot is exchanged with __syncwarp only.  Sorting the threads of a
+// tile by airframe class (warp-uniform control law / rotor count) was measured and rejected: it removed
+// 2.6 % of the issued instructions (divergence only idles 4.5 % of the lanes in the 8 quad + 8 hexa env)
+// but needed a CTA-wide barrier per substep and ran 7 % slower (profiles/r01_notes.md).
 #pragma once
 #include "ds_control.cuh"
 #include "ds_device.cuh"
@@ -39,25 +39,27 @@ __device__ __forceinline__ float ds_warp_min(float v) {
   return v;
 }
 
-struct StatAcc { float n_ctrl, err2, sat, wls_slow, wls_fail, nonfinite, min_z, done; };
+// Rollout statistics: per-thread accumulators live in SHARED memory (one column per thread) so they cost no
+// registers across the persistent tile loop; one warp-shuffle reduction + atomics per CTA at the end.
+enum { ST_NCTRL = 0, ST_ERR2, ST_SAT, ST_WLS_SLOW, ST_WLS_FAIL, ST_NONFINITE, ST_MINZ, ST_DONE, ST_COUNT };
 
-__device__ __forceinline__ void ds_flush_stats(const StatAcc& s, double* stats) {
-  float v0 = ds_warp_sum(s.n_ctrl), v1 = ds_warp_sum(s.err2), v2 = ds_warp_sum(s.sat), v3 = ds_warp_sum(s.wls_slow);
-  float v4 = ds_warp_sum(s.wls_fail), v5 = ds_warp_sum(s.nonfinite), v6 = ds_warp_min(s.min_z), v7 = ds_warp_sum(s.done);
-  if ((threadIdx.x & 31) == 0) {
-    if (v0 != 0.f) atomicAdd(stats + 0, (double)v0);
-    if (v1 != 0.f) atomicAdd(stats + 1, (double)v1);
-    if (v2 != 0.f) atomicAdd(stats + 2, (double)v2);
-    if (v3 != 0.f) atomicAdd(stats + 3, (double)v3);
-    if (v4 != 0.f) atomicAdd(stats + 4, (double)v4);
-    if (v5 != 0.f) atomicAdd(stats + 5, (double)v5);
-    if (v7 != 0.f) atomicAdd(stats + 7, (double)v7);
+__device__ __forceinline__ void ds_flush_stats(const float* sh_stat, double* stats) {
+  const int t = threadIdx.x;
+  float v[ST_COUNT];
+#pragma unroll
+  for (int i = 0; i < ST_COUNT; ++i) v[i] = sh_stat[i * DS_TILE + t];
+#pragma unroll
+  for (int i = 0; i < ST_COUNT; ++i) v[i] = (i == ST_MINZ) ? ds_warp_min(v[i]) : ds_warp_sum(v[i]);
+  if ((t & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i)
+      if (i != ST_MINZ && v[i] != 0.f) atomicAdd(stats + i, (double)v[i]);
     // min altitude: doubles order like their bit patterns for non-negative values only, so use a CAS loop
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(stats + 6);
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(stats + ST_MINZ);
     unsigned long long old = *p;
-    while (__longlong_as_double((long long)old) > (double)v6) {
+    while (__longlong_as_double((long long)old) > (double)v[ST_MINZ]) {
       unsigned long long assumed = old;
-      old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong((double)v6));
+      old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong((double)v[ST_MINZ]));
       if (old == assumed) break;
     }
   }
@@ -83,82 +85,85 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, int v, in
 }
 
 template <int INTEG, bool DW, bool NU6, bool WARPSYNC, int MODE>
-__global__ void __launch_bounds__(DS_TILE, 2) ds_step_kernel(const DsArgs a) {
+__global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsArgs a) {
   __shared__ __align__(16) DsTypeDev sh_types[DS_MAX_TYPES_DEV];
   __shared__ uint8_t sh_slot_type[32];
   __shared__ __align__(16) float4 sh_pos[DW ? 2 * DS_DW_ROWS : 1];
+  __shared__ float sh_stat[ST_COUNT * DS_TILE];
   ds_load_types(a, sh_types);
   if (threadIdx.x < 32) sh_slot_type[threadIdx.x] = (threadIdx.x < a.D) ? a.slot_type[threadIdx.x] : 0;
+  const bool stats_on = (a.flags & 8u) != 0;
+  if (stats_on) {
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i) sh_stat[i * DS_TILE + threadIdx.x] = (i == ST_MINZ) ? 3.0e38f : 0.f;
+  }
   __syncthreads();
 
   constexpr int NU = NU6 ? 6 : 4;
   const int tid = threadIdx.x;
-  const int lv_raw = a.tile_map[tid];
-  const bool lane_ok = lv_raw != 0xFFFF;
-  const int lv = lane_ok ? lv_raw : 0;  // idle lanes shadow local vehicle 0 (no stores) so barriers stay uniform
+  const bool lane_ok = tid < a.tile_v;
+  const int lv = lane_ok ? tid : 0;  // idle lanes shadow local vehicle 0 (no stores) so barriers stay uniform
   const int slot = lv % a.D;
   const int env_row0 = (lv / a.D) * (a.D + DS_DW_PAD);  // padded row of the env's slot 0 in the downwash snapshot
   const int my_row = env_row0 + slot;
   const int type_id = sh_slot_type[slot];
   const DsTypeDev& tp = sh_types[type_id];
-  StatAcc st = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 3.0e38f, 0.f};
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int v = tile * a.tile_v + lv;
     const bool valid = lane_ok && v < a.n;
     const int vv = valid ? v : 0;
 
-    float4 P = a.s_pos[vv], Q = a.s_quat[vv], V = a.s_vel[vv], W = a.s_om[vv];
+    // ---- physics inputs.  The controller memory (last_vel, last_rates, cmd) is loaded only when the control
+    // law runs, so that it does not occupy registers during the K substeps.
+    const float4 P = a.s_pos[vv], Q = a.s_quat[vv], V = a.s_vel[vv], W = a.s_om[vv];
     PhysState s = {P.x, P.y, P.z, Q.x, Q.y, Q.z, Q.w, V.x, V.y, V.z, W.x, W.y, W.z};
     float prev_rpm_sum = V.w;
+    float lthrust = P.w;
     int wp = __float_as_int(W.w);
+
     CtrlMem m;
-    uint32_t done_bits = 0;
-    float4 LV = make_float4(0.f, 0.f, 0.f, 0.f), LR = LV;
-    if (MODE == 0) {
-      LV = a.s_lv[vv]; LR = a.s_lr[vv];
-      float4 C0 = a.s_c0[vv];
-      m.lvx = LV.x; m.lvy = LV.y; m.lvz = LV.z; m.lrx = LR.x; m.lry = LR.y; m.lrz = LR.z; m.lthrust = P.w;
-      m.cmd[0] = C0.x; m.cmd[1] = C0.y; m.cmd[2] = C0.z; m.cmd[3] = C0.w;
-      if (NU6) { float2 C1 = a.s_c1[vv]; m.cmd[4] = C1.x; m.cmd[5] = C1.y; } else { m.cmd[4] = m.cmd[5] = 0.f; }
-      done_bits = __float_as_uint(LV.w);
-    } else {
-      done_bits = __float_as_uint(a.s_lv[vv].w);
-    }
-
-    // ---- the action the physics applies
-    float act[6];
-    if (MODE == 1) {  // external action, clipped (CtrlAviary.py:258-263)
-      const float* ea = a.ext_action + (size_t)vv * 6;
-#pragma unroll
-      for (int i = 0; i < NU; ++i) act[i] = ds_clampf(ea[i], tp.rotor[i].pmin, tp.rotor[i].pmax);
-    } else if (a.use_act) {  // first step after reset: the caller's initial action (fly_INDI.py:214)
-      float4 A0 = a.s_a0[vv];
-      act[0] = A0.x; act[1] = A0.y; act[2] = A0.z; act[3] = A0.w;
-      if (NU6) { float2 A1 = a.s_a1[vv]; act[4] = A1.x; act[5] = A1.y; }
-#pragma unroll
-      for (int i = 0; i < NU; ++i) act[i] = ds_clampf(act[i], tp.rotor[i].pmin, tp.rotor[i].pmax);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NU; ++i) act[i] = m.cmd[i];  // already clipped by the controller (INDIControl.py:487)
-    }
-
     CtrlOut o = {0.f, 0.f, 0.f, 0.f, 0, 0};
-    float perr = LR.w;
-    auto control = [&]() {
+    float perr = 0.f;
+    uint32_t done_bits = 0;
+    auto control = [&]() {  // INDIControl.computeControl on the resident state
+      const float4 LV = a.s_lv[vv], LR = a.s_lr[vv], C0 = a.s_c0[vv];
+      m.lvx = LV.x; m.lvy = LV.y; m.lvz = LV.z; m.lrx = LR.x; m.lry = LR.y; m.lrz = LR.z; m.lthrust = lthrust;
+      m.cmd[0] = C0.x; m.cmd[1] = C0.y; m.cmd[2] = C0.z; m.cmd[3] = C0.w;
+      if (NU6) { const float2 C1 = a.s_c1[vv]; m.cmd[4] = C1.x; m.cmd[5] = C1.y; } else { m.cmd[4] = m.cmd[5] = 0.f; }
+      done_bits = __float_as_uint(LV.w);
       CtrlState cs = {s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, s.wx, s.wy, s.wz};
       CtrlTarget t = ds_fetch_target(a, vv, wp);
       ds_indi_control<NU6>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, m, o, false);
       perr = sqrtf(o.pex * o.pex + o.pey * o.pey + o.pez * o.pez);
+      lthrust = m.lthrust;
     };
 
+    // ---- the action the physics applies
+    float act[6];
     if (MODE == 0 && a.order == 1) {  // VelocityAviary order: control, then physics with the new command
       control();
 #pragma unroll
       for (int i = 0; i < NU; ++i) act[i] = m.cmd[i];
+    } else if (MODE == 1) {  // external action, clipped (CtrlAviary.py:258-263)
+      const float* ea = a.ext_action + (size_t)vv * 6;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) act[i] = ds_clampf(ea[i], tp.rotor[i].pmin, tp.rotor[i].pmax);
+    } else if (a.use_act) {  // first step after reset: the caller's initial action (fly_INDI.py:214)
+      const float4 A0 = a.s_a0[vv];
+      act[0] = A0.x; act[1] = A0.y; act[2] = A0.z; act[3] = A0.w;
+      if (NU6) { const float2 A1 = a.s_a1[vv]; act[4] = A1.x; act[5] = A1.y; }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) act[i] = ds_clampf(act[i], tp.rotor[i].pmin, tp.rotor[i].pmax);
+    } else {  // the resident controller command, already clipped by the controller (INDIControl.py:487)
+      const float4 C0 = a.s_c0[vv];
+      act[0] = C0.x; act[1] = C0.y; act[2] = C0.z; act[3] = C0.w;
+      if (NU6) { const float2 C1 = a.s_c1[vv]; act[4] = C1.x; act[5] = C1.y; }
     }
+
     ds_physics<INTEG, DW, NU6, WARPSYNC>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum);
     if (MODE == 0 && a.order == 0) control();
+    if (MODE == 1) done_bits = __float_as_uint(a.s_lv[vv].w);
 
     // ---- done predicate on the fresh state (fly_INDI_TrajectoryTrack.py:249-250)
     if (a.goal_en) {
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(DS_TILE, 2) ds_step_kernel(const DsArgs a) {
     if (a.time_hit) done_bits |= 4u;
 
     if (valid) {
-      a.s_pos[v] = make_float4(s.px, s.py, s.pz, MODE == 0 ? m.lthrust : P.w);
+      a.s_pos[v] = make_float4(s.px, s.py, s.pz, lthrust);
       a.s_quat[v] = make_float4(s.qx, s.qy, s.qz, s.qw);
       a.s_vel[v] = make_float4(s.vx, s.vy, s.vz, prev_rpm_sum);
       a.s_om[v] = make_float4(s.wx, s.wy, s.wz, __int_as_float(wp));
@@ -179,30 +184,29 @@ __global__ void __launch_bounds__(DS_TILE, 2) ds_step_kernel(const DsArgs a) {
         a.s_c0[v] = make_float4(m.cmd[0], m.cmd[1], m.cmd[2], m.cmd[3]);
         if (NU6) a.s_c1[v] = make_float2(m.cmd[4], m.cmd[5]);
       } else {
-        float4 lv = a.s_lv[v];
-        lv.w = __uint_as_float(done_bits);
-        a.s_lv[v] = lv;
+        reinterpret_cast<float*>(a.s_lv + v)[3] = __uint_as_float(done_bits);
       }
       if (a.store_act) {
         a.s_a0[v] = make_float4(act[0], act[1], act[2], act[3]);
         if (NU6) a.s_a1[v] = make_float2(act[4], act[5]);
       }
-      if (a.flags & 8u) {
+      if (stats_on) {
+        float* st = sh_stat + tid;
         if (MODE == 0) {
-          st.n_ctrl += 1.f;
-          st.err2 += perr * perr;
-          st.sat += (float)o.sat;
-          st.wls_slow += (o.wls_iter != 1 && o.wls_iter != 0) ? 1.f : 0.f;
-          st.wls_fail += (o.wls_iter < 0) ? 1.f : 0.f;
+          st[ST_NCTRL * DS_TILE] += 1.f;
+          st[ST_ERR2 * DS_TILE] += perr * perr;
+          if (o.sat) st[ST_SAT * DS_TILE] += (float)o.sat;
+          if (o.wls_iter != 1 && o.wls_iter != 0) st[ST_WLS_SLOW * DS_TILE] += 1.f;
+          if (o.wls_iter < 0) st[ST_WLS_FAIL * DS_TILE] += 1.f;
         }
-        bool fin = isfinite(s.px) && isfinite(s.py) && isfinite(s.pz) && isfinite(s.qw) && isfinite(s.vx) && isfinite(s.wx);
-        st.nonfinite += fin ? 0.f : 1.f;
-        st.min_z = fminf(st.min_z, s.pz);
-        st.done += done_bits ? 1.f : 0.f;
+        const bool fin = isfinite(s.px) && isfinite(s.py) && isfinite(s.pz) && isfinite(s.qw) && isfinite(s.vx) && isfinite(s.wx);
+        if (!fin) st[ST_NONFINITE * DS_TILE] += 1.f;
+        st[ST_MINZ * DS_TILE] = fminf(st[ST_MINZ * DS_TILE], s.pz);
+        if (done_bits) st[ST_DONE * DS_TILE] += 1.f;
       }
     }
   }
-  if (a.flags & 8u) ds_flush_stats(st, a.stats);
+  if (stats_on) ds_flush_stats(sh_stat, a.stats);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -65,8 +65,15 @@ __device__ __forceinline__ void ds_downwash_pair(float& acc, const float4 o, flo
                                                  float k3) {
   const float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
   const float d2 = fmaf(dy, dy, dx * dx);
+#ifdef DS_EXP_PAIR2  // experiment: 2 MUFU + 3 more FMUL/FADD per pair
+  const float bt = fmaf(k2, dz, k3) + 1e-30f;
+  const float t = ds_rcp(dz * bt);
+  const float idz = t * bt, ib = t * dz;
+  const float idz2 = idz * idz;
+#else
   const float ib = ds_rcp(fmaf(k2, dz, k3));   // 1 / beta'
   const float idz2 = ds_rcp(dz * dz);          // 1 / dz^2
+#endif
   const float w = idz2 * ds_ex2((ib * ib) * -d2);
   asm("{\n\t.reg .pred p;\n\t"
       "setp.gt.f32 p, %1, 0f00000000;\n\t"
@@ -79,8 +86,12 @@ __device__ __forceinline__ void ds_downwash_pair(float& acc, const float4 o, flo
 __device__ __forceinline__ float ds_downwash_sum(const float4* __restrict__ row, int D, float px, float py, float pz,
                                                  float k2, float k3) {
   float acc = 0.f;
+#ifndef DS_PAIR_UNROLL
+#define DS_PAIR_UNROLL 16
+#endif
+  constexpr int kUnroll = DS_PAIR_UNROLL;
   if (D == 16) {  // BASELINE configs[3]/[4]
-#pragma unroll
+#pragma unroll kUnroll
     for (int j = 0; j < 16; ++j) ds_downwash_pair(acc, row[j], px, py, pz, k2, k3);
   } else {
 #pragma unroll 4
@@ -96,25 +107,25 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
                                            const float* act, PhysState& s, float& prev_rpm_sum) {
   constexpr int NU = NU6 ? 6 : 4;
   const float dt = a.dt;
+#ifdef DS_EXP_FX  // experiment: flags as compile-time constants (straight-line substep body)
+  constexpr bool gnd = true, drag = true;
+#else
   const bool gnd = (a.flags & 1u) != 0, drag = (a.flags & 2u) != 0;
-  const bool has_rc = (INTEG == 0) && (tp.has_rc != 0);  // per type: warp-uniform when the tile map sorts by class
-  const int n_u = tp.n_u;
+#endif
+  const bool has_rc = (INTEG == 0) && (tp.has_rc != 0);  // per type (quads of the shipped URDFs have none)
 
   // ---- per control step: rotor thrusts and the constant part of the body wrench
   float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
   float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
 #pragma unroll
-  for (int i = 0; i < NU; ++i) {
-    Tg[i] = 0.f;
-    if (i < n_u) {
-      const DsRotorDev& r = tp.rotor[i];
-      float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
-      rpm_sum += rpm;
-      float T = tp.kf * rpm * rpm;                // :1515
-      Tg[i] = T * tp.gnd_k;
-      F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
-      t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
-    }
+  for (int i = 0; i < NU; ++i) {  // rotors beyond n_u have scale = const = 0 -> T = 0
+    const DsRotorDev& r = tp.rotor[i];
+    float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
+    rpm_sum += rpm;
+    float T = tp.kf * rpm * rpm;                // :1515
+    Tg[i] = T * tp.gnd_k;
+    F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
+    t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
   }
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
 
@@ -144,17 +155,21 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
       bool gate;
       if (INTEG == 1) gate = (fabsf(roll) < 0.5f * DS_PI_F) && (fabsf(pitch) < 0.5f * DS_PI_F);
       else gate = (R.m22 > 0.f) && (fabsf(R.m20) < DS_GIMBAL);  // |roll| < pi/2 <=> cos(roll)cos(pitch) > 0
+#ifdef DS_EXP_FX
+      const float gsel = gate ? 1.f : 0.f;
+      {
+#else
+      const float gsel = 1.f;
       if (gate) {
+#endif
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          if (i < n_u) {
-            const DsRotorDev& r = tp.rotor[i];
-            float h = fmaf(R.m20, r.rx, fmaf(R.m21, r.ry, fmaf(R.m22, r.rz, cz)));
-            float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
-            float g = (Tg[i] * ih) * ih;
-            Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
-            tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
-          }
+          const DsRotorDev& r = tp.rotor[i];
+          float h = fmaf(R.m20, r.rx, fmaf(R.m21, r.ry, fmaf(R.m22, r.rz, cz)));
+          float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
+          float g = (Tg[i] * ih) * (ih * gsel);
+          Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
+          tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
         }
       }
     }

@@ -67,3 +67,60 @@ def algorithmic_bytes_per_control_step(n_u: int, per_vehicle_targets: bool = Tru
 def hetero16_bytes_per_control_step() -> float:
     """Mean over the 8 quads + 8 hexas of an env: (233 + 249) / 2 = 241 B."""
     return 0.5 * (algorithmic_bytes_per_control_step(4) + algorithmic_bytes_per_control_step(6))
+
+
+# --------------------------------------------------------------------------------------------
+# single-type swarms of BASELINE configs[1] / configs[2] at scale (one drone per env)
+# --------------------------------------------------------------------------------------------
+def circle_table(num_wp: int = 1440, radius: float = 1.2, z: float = 0.6) -> np.ndarray:
+    """examples/fly_hexa_6DOF.py:157-166,224-226: circle of ``radius`` flown twice over NUM_WP waypoints,
+    rows = pos3 vel3 acc3 yaw (vel / acc / yaw zero, as the script passes none)."""
+    i = np.arange(num_wp)
+    tab = np.zeros((num_wp, 10))
+    tab[:, 0] = radius * np.cos((i / num_wp) * (4 * np.pi) + np.pi / 2)
+    tab[:, 1] = radius * np.sin((i / num_wp) * (4 * np.pi) + np.pi / 2) - radius
+    tab[:, 2] = z
+    return tab
+
+
+def single_type(name: str, n_envs: int, seed: int = 0, env_offset: int = 0):
+    """(models, K, flags, pos0[E,1,3], action0[E,1,6], table[num_wp,10], wp0[E]) of
+
+    ``"traj_quad"``  configs[1]: robobee tracking a waypoint table, K = 2 (96 Hz control), no add-ons.  The
+                     table is a 1200-row stand-in with the shape of the reference's 3-gate trajectory
+                     (the exact trajGenerator table lives in tests/golden/traj_3gates.npz);
+    ``"hexa_circle"`` configs[2]: hexa_6DOF on the fly_hexa_6DOF.py circle, K = 2, ground effect + drag;
+    ``"quad_k8"``    robobee hover-table, K = 8, no add-ons (the plain dynamics + INDI path of configs[4]).
+    """
+    e = (np.arange(n_envs, dtype=np.uint64) + np.uint64(env_offset))[:, None]
+    idx = e * np.uint64(3) + np.arange(3, dtype=np.uint64)[None, :]
+    noise = (_hash01(idx, seed) - 0.5) * 0.1  # U(-0.05, 0.05)
+    if name == "traj_quad":
+        models, K, flags = ["robobee"], 2, dict(ground=False, drag=False, downwash=False)
+        t = np.linspace(0.0, 1.0, 1200)
+        tab = np.zeros((1200, 10))
+        tab[:, 0] = -3.0 + 6.0 * t
+        tab[:, 1] = np.sin(np.pi * t)
+        tab[:, 2] = 2.0 + 3.0 * np.sin(np.pi * t)
+        tab[:, 3:6] = np.gradient(tab[:, 0:3], 1.0 / 96.0, axis=0)
+        tab[:, 6:9] = np.gradient(tab[:, 3:6], 1.0 / 96.0, axis=0)
+        base, cmd0 = np.array([-3.0, 0.0, 2.0]), 0.4
+    elif name == "hexa_circle":
+        models, K, flags = ["hexa_6DOF"], 2, dict(ground=True, drag=True, downwash=False)
+        tab = circle_table()
+        base, cmd0 = np.array([0.0, 0.0, 0.6]), 0.1
+    elif name == "quad_k8":
+        models, K, flags = ["robobee"], 8, dict(ground=False, drag=False, downwash=False)
+        tab = np.zeros((720, 10))
+        tab[:, 2] = 0.5
+        tab[:, 9] = 0.4 + np.arange(720) / 200.0  # fly_INDI.py:165-167
+        base, cmd0 = np.array([0.0, 0.0, 0.5]), 0.4
+    else:
+        raise KeyError(name)
+    # every env starts ON the trajectory at its own waypoint (env index staggers the table rows read per step)
+    wp0 = ((np.arange(n_envs, dtype=np.int64) + env_offset) % tab.shape[0]).astype(np.int32)
+    del base
+    pos0 = (tab[wp0, 0:3] + noise).reshape(n_envs, 1, 3)
+    act0 = np.zeros((n_envs, 1, 6))
+    act0[:, 0, : (6 if "hexa" in models[0] else 4)] = cmd0
+    return models, K, flags, pos0, act0, tab, wp0

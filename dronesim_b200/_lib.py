@@ -92,6 +92,7 @@ SYMBOLS = {
     "ds_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
     "ds_stats_reset": (C.c_int, [_H, C.c_void_p]),
     "ds_step_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_rollout_host": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                C.c_void_p]),
     "ds_debug_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),

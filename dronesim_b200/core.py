@@ -261,6 +261,14 @@ class SwarmCore:
         L.check(L.lib().ds_step_host(self._h, C.c_void_p(host_pos_yaw.data_ptr()),
                                      self._p(host_obs), self._p(host_done), self._stream()), self._h)
 
+    def rollout_host(self, host_pos_yaw: torch.Tensor, host_done: Optional[torch.Tensor] = None):
+        """``host_pos_yaw`` [T, N, 4] pinned float32, ``host_done`` [T, E] pinned uint8 or None: T control steps with the
+        H2D / D2H copies pipelined against the compute (``ds_rollout_host``); synchronises."""
+        T = int(host_pos_yaw.shape[0])
+        assert host_pos_yaw.dtype == torch.float32 and host_pos_yaw.is_contiguous() and host_pos_yaw.numel() == T * self.N * 4
+        L.check(L.lib().ds_rollout_host(self._h, C.c_void_p(host_pos_yaw.data_ptr()), T, self._p(host_done), self._stream()),
+                self._h)
+
     # ------------------------------------------------------------------ state access
     def views(self) -> dict:
         """Zero-copy torch views of the resident state (valid until ``close``)."""

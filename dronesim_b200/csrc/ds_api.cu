@@ -38,6 +38,11 @@ struct ds_handle {
   float4* d_host_tgt = nullptr;
   float* d_obs = nullptr;
   uint8_t* d_done_env = nullptr;
+  // ds_rollout_host: double-buffered targets / done flags, copy streams, events
+  float4* d_roll_tgt[2] = {nullptr, nullptr};
+  uint8_t* d_roll_done[2] = {nullptr, nullptr};
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
   uint8_t slot_type[DS_MAX_DRONES_PER_ENV];
 };
 
@@ -67,9 +72,17 @@ extern "C" int64_t ds_launch_count(ds_handle* h) { return h ? h->launches : 0; }
 static void free_all(ds_handle* h) {
   void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
                   h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
-                  h->d_host_tgt, h->d_obs, h->d_done_env};
+                  h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
+                  h->d_roll_done[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+    if (h->ev_computed[b]) cudaEventDestroy(h->ev_computed[b]);
+    if (h->ev_drained[b]) cudaEventDestroy(h->ev_drained[b]);
+  }
+  if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
+  if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
 }
 
 extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
@@ -508,6 +521,55 @@ extern "C" int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host
     if (host_done_env) CK(cudaMemcpyAsync(host_done_env, h->d_done_env, (size_t)h->cfg.n_envs, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  return DS_OK;
+}
+
+extern "C" int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t n_steps, uint8_t* host_done_env,
+                               void* stream) {
+  if (!h || !host_pos_yaw || n_steps <= 0) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n, E = (size_t)h->cfg.n_envs;
+  if (!h->st_h2d) {
+    CK(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaMalloc((void**)&h->d_roll_tgt[b], (size_t)h->n_pad * 16));
+      CK(cudaMalloc((void**)&h->d_roll_done[b], E));
+      CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_computed[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_drained[b], cudaEventDisableTiming));
+    }
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    const int b = i & 1;
+    // targets of step i -> device buffer b (free once step i-2 has consumed it)
+    if (i >= 2) CK(cudaStreamWaitEvent(h->st_h2d, h->ev_computed[b], 0));
+    CK(cudaMemcpyAsync(h->d_roll_tgt[b], host_pos_yaw + (size_t)i * n * 4, n * 16, cudaMemcpyHostToDevice, h->st_h2d));
+    CK(cudaEventRecord(h->ev_copied[b], h->st_h2d));
+    CK(cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+    ds_targets t;
+    memset(&t, 0, sizeof(t));
+    t.mode = 0;
+    t.pos_yaw = (const float*)h->d_roll_tgt[b];
+    int rc = ds_step(h, &t, 1, DS_ORDER_PHYSICS_THEN_CONTROL, stream);
+    if (rc != DS_OK) return rc;
+    if (host_done_env) {
+      if (i >= 2) CK(cudaStreamWaitEvent(st, h->ev_drained[b], 0));  // done buffer b has left for the host
+      rc = ds_get_obs(h, nullptr, nullptr, h->d_roll_done[b], nullptr, stream);
+      if (rc != DS_OK) return rc;
+    }
+    CK(cudaEventRecord(h->ev_computed[b], st));
+    if (host_done_env) {
+      CK(cudaStreamWaitEvent(h->st_d2h, h->ev_computed[b], 0));
+      CK(cudaMemcpyAsync(host_done_env + (size_t)i * E, h->d_roll_done[b], E, cudaMemcpyDeviceToHost, h->st_d2h));
+      CK(cudaEventRecord(h->ev_drained[b], h->st_d2h));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(h->st_h2d));
+  CK(cudaStreamSynchronize(h->st_d2h));
   return DS_OK;
 }
 

@@ -65,6 +65,39 @@ __device__ __forceinline__ void ds_flush_stats(const float* sh_stat, double* sta
   }
 }
 
+// Bulk L2 prefetch (TMA unit, no shared-memory staging): one instruction pulls `bytes` (multiple of 16) of a
+// contiguous slab into L2.  One thread per CTA issues these for the CTA's NEXT tile at the start of the
+// current one, so the DRAM reads of tile i+1 overlap the K substeps of tile i and the tile-start / control-
+// phase loads become L2 hits instead of exposed DRAM latency.
+__device__ __forceinline__ void ds_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <bool NU6, int MODE>
+__device__ __forceinline__ void ds_prefetch_tile(const DsArgs& a, int tile) {
+  const long long v0 = (long long)tile * a.tile_v;
+  const int cnt = (int)min((long long)DS_TILE, (long long)a.n - v0);  // vehicles of the tile that exist
+  if (cnt <= 0) return;
+  const uint32_t b16 = (uint32_t)cnt * 16u;
+  ds_prefetch_l2(a.s_pos + v0, b16); ds_prefetch_l2(a.s_quat + v0, b16);
+  ds_prefetch_l2(a.s_vel + v0, b16); ds_prefetch_l2(a.s_om + v0, b16);
+  if (MODE == 0) {
+    ds_prefetch_l2(a.s_lv + v0, b16); ds_prefetch_l2(a.s_lr + v0, b16); ds_prefetch_l2(a.s_c0 + v0, b16);
+    if (NU6) {  // float2 array: keep the slab 16-byte aligned and inside the allocation
+      const long long v0e = v0 & ~1LL;
+      const uint32_t b8 = (uint32_t)(((cnt + (int)(v0 - v0e)) * 8) & ~15);
+      if (b8) ds_prefetch_l2(a.s_c1 + v0e, b8);
+    }
+    if (a.tmode == 0) {
+      ds_prefetch_l2(a.t_pos + v0, b16);
+      if (a.t_vel) ds_prefetch_l2(a.t_vel + v0, b16);
+      if (a.t_acc) ds_prefetch_l2(a.t_acc + v0, b16);
+    } else if (a.t_off) {
+      ds_prefetch_l2(a.t_off + v0, b16);
+    }
+  }
+}
+
 __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, int v, int& wp) {
   CtrlTarget t;
   if (a.tmode == 0) {
@@ -113,6 +146,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
     const int v = tile * a.tile_v + lv;
     const bool valid = lane_ok && v < a.n;
     const int vv = valid ? v : 0;
+    if (tid == 0 && tile + (int)gridDim.x < a.n_tiles) ds_prefetch_tile<NU6, MODE>(a, tile + gridDim.x);
 
     // ---- physics inputs.  The controller memory (last_vel, last_rates, cmd) is loaded only when the control
     // law runs, so that it does not occupy registers during the K substeps.

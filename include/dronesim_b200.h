@@ -197,6 +197,14 @@ int ds_stats_reset(ds_handle* h, void* stream);
  * HOST memory (pinned buffers give the best overlap).  Synchronises the stream before returning. */
 int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host_obs, uint8_t* host_done_env, void* stream);
 
+/* n_steps control steps driven from the host with the copies PIPELINED against the compute: the targets of
+ * step i+1 (HOST [n_steps][N][4], pinned) travel to the device on a copy stream while step i runs, and the
+ * per-env done flags of step i (HOST [n_steps][n_envs], pinned, or NULL) travel back while step i+1 runs.
+ * Use when the set-points of the next steps are known ahead (the reference examples' TARGET_POS tables,
+ * fly_INDI_TrajectoryTrack.py:133-160).  Every step still pays its own H2D / D2H; they just overlap.
+ * Synchronises before returning. */
+int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t n_steps, uint8_t* host_done_env, void* stream);
+
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* The 6-DOF allocation alone: wls_alloc(v, MIN-cmd, MAX-cmd, G1/0.05, None, None, Wv, 1, None)
  * (INDIControl_6DOF.py:607-628 -> wls_alloc.py:125-350) for n independent problems of type type_id.

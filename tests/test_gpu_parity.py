@@ -365,3 +365,44 @@ def test_integer_bookkeeping_and_done_flags():
     _, _, dn, _ = core.get_obs()
     assert dn.cpu().numpy().all()  # time limit reached everywhere
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# host-buffer entry points: pipelined rollout == per-step synchronous calls == device-resident steps
+# ------------------------------------------------------------------------------------------
+def test_host_entry_points_are_equivalent():
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.workloads import hetero16
+
+    E, T = 40, 5  # 640 vehicles: 2.5 tiles (ragged last tile)
+    models, K, flags, pos0, act0, tgt = hetero16(E)
+    rng = np.random.default_rng(9)
+    seq = np.repeat(tgt[None].astype(np.float32), T, axis=0)
+    seq[:, :, :3] += rng.uniform(-0.1, 0.1, (T, E * 16, 3)).astype(np.float32)
+    h_seq = torch.from_numpy(seq).pin_memory()
+    outs = []
+    for mode in ("rollout", "per_step", "device"):
+        core = SwarmCore(models, E, aggregate_phy_steps=K, z_min=1.99, **flags)
+        core.reset(pos0, action0=act0)
+        done = torch.zeros((T, E), dtype=torch.uint8).pin_memory()
+        if mode == "rollout":
+            core.rollout_host(h_seq, done)
+        elif mode == "per_step":
+            for t in range(T):
+                core.step_host(h_seq[t], None, done[t])
+        else:
+            for t in range(T):
+                core.step(core.targets_per_vehicle(seq[t]), 1)
+                _, _, dn, _ = core.get_obs(state=False, neighbors=False)
+                done[t] = dn.cpu()
+        torch.cuda.synchronize()
+        v = core.views()
+        outs.append((v["pos"].cpu().numpy().copy(), v["quat"].cpu().numpy().copy(), core.cmd().cpu().numpy().copy(),
+                     done.numpy().copy(), core.step_counter))
+        core.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0][:4], o[:4]):
+            np.testing.assert_array_equal(a, b)
+        assert o[4] == outs[0][4] == T * K
+    assert outs[0][3].any() and not outs[0][3].all()  # the floor predicate fires for the low quads only

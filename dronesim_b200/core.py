@@ -72,6 +72,7 @@ def type_params(vt: VehicleType, composite: bool) -> L.ds_type_params:
     # controller reset values: INDIControl.py:127-129 vs INDIControl_6DOF.py:232-234
     p.init_cmd = 0.5 if vt.law == LAW_6DOF else 0.0
     p.init_thrust = 0.3 if vt.law == LAW_6DOF else 0.0
+    p.max_speed_kmh = float(vt.MAX_SPEED_KMH)
     return p
 
 
@@ -186,6 +187,15 @@ class SwarmCore:
         t.vel = v.data_ptr() if v is not None else None
         t.acc = a.data_ptr() if a is not None else None
         t._keep = (p, v, a)
+        return t
+
+    def targets_velocity(self, vel_action) -> L.ds_targets:
+        """mode 2: ``vel_action`` [N,4] = VelocityAviary actions (direction xyz, fraction of the speed limit)."""
+        t = L.ds_targets()
+        v = self._dev4(vel_action, "vel_action")
+        t.mode = 2
+        t.vel = v.data_ptr()
+        t._keep = (v,)
         return t
 
     def targets_table(self, table, offset=None, advance: bool = True) -> L.ds_targets:

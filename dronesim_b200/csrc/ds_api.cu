@@ -197,6 +197,7 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     for (int i = 0; i < 3; ++i) { d.att[i] = (float)p.att_gain[i]; d.rate[i] = (float)p.rate_gain[i]; }
     d.n_u = p.n_u;
     d.law = p.law;
+    d.speed_limit = (float)(p.max_speed_kmh * (1000.0 / 3600.0));
     double rpm0 = 0.0;
     for (int i = 0; i < p.n_u; ++i) {
       DsRotorDev& r = d.rotor[i];
@@ -326,6 +327,9 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
     if (!t->table || t->num_wp <= 0) return DS_ERR_INVALID;
     a.t_table = (const float4*)t->table; a.t_off = (const float4*)t->offset;
     a.num_wp = t->num_wp; a.advance_wp = t->advance_wp;
+  } else if (t->mode == 2) {
+    if (!t->vel) return DS_ERR_INVALID;
+    a.t_vel = (const float4*)t->vel;
   } else {
     return DS_ERR_INVALID;
   }

@@ -92,15 +92,27 @@ __device__ __forceinline__ void ds_prefetch_tile(const DsArgs& a, int tile) {
       ds_prefetch_l2(a.t_pos + v0, b16);
       if (a.t_vel) ds_prefetch_l2(a.t_vel + v0, b16);
       if (a.t_acc) ds_prefetch_l2(a.t_acc + v0, b16);
+    } else if (a.tmode == 2) {
+      ds_prefetch_l2(a.t_vel + v0, b16);
     } else if (a.t_off) {
       ds_prefetch_l2(a.t_off + v0, b16);
     }
   }
 }
 
-__device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, int v, int& wp) {
+__device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsTypeDev& tp, const CtrlState& cs, int v,
+                                                      int& wp) {
   CtrlTarget t;
-  if (a.tmode == 0) {
+  if (a.tmode == 2) {  // VelocityAviary._preprocessAction (VelocityAviary.py:236-257)
+    float4 q = __ldg(a.t_vel + v);
+    float n2 = q.x * q.x + q.y * q.y + q.z * q.z;
+    float k = (n2 != 0.f) ? tp.speed_limit * fabsf(q.w) / sqrtf(n2) : 0.f;
+    float roll, pitch, yaw;
+    ds_euler(cs.qx, cs.qy, cs.qz, cs.qw, roll, pitch, yaw);
+    t.x = cs.px; t.y = cs.py; t.z = cs.pz; t.yaw = yaw;  // hold position and yaw (state[0:3], state[9])
+    t.vx = k * q.x; t.vy = k * q.y; t.vz = k * q.z;
+    t.ax = t.ay = t.az = 0.f;
+  } else if (a.tmode == 0) {
     float4 p = __ldg(a.t_pos + v);
     t.x = p.x; t.y = p.y; t.z = p.z; t.yaw = p.w;
     t.vx = t.vy = t.vz = t.ax = t.ay = t.az = 0.f;
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
       if (NU6) { const float2 C1 = a.s_c1[vv]; m.cmd[4] = C1.x; m.cmd[5] = C1.y; } else { m.cmd[4] = m.cmd[5] = 0.f; }
       done_bits = __float_as_uint(LV.w);
       CtrlState cs = {s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, s.wx, s.wy, s.wz};
-      CtrlTarget t = ds_fetch_target(a, vv, wp);
+      CtrlTarget t = ds_fetch_target(a, tp, cs, vv, wp);
       ds_indi_control<NU6>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, m, o, false);
       perr = sqrtf(o.pex * o.pex + o.pey * o.pey + o.pez * o.pez);
       lthrust = m.lthrust;
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(DS_TILE) ds_control_kernel(const DsArgs a) {
     CtrlOut o = {0.f, 0.f, 0.f, 0.f, 0, 0};
     int wp = __float_as_int(W.w);
     if (MODE == 0) {
-      CtrlTarget t = ds_fetch_target(a, v, wp);
+      CtrlTarget t = ds_fetch_target(a, tp, cs, v, wp);
       ds_indi_control<NU6>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, m, o, true);
     } else {  // INDIControl._INDIRateControl (INDIControl.py:413-490)
       float4 rt = a.rate_thrust[v];

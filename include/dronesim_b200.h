@@ -112,16 +112,20 @@ typedef struct ds_type_params {
   double wls_gamma;                     /* gamma_sq of wls_alloc.py:125 */
   double init_cmd;                      /* controller reset: 0.0 (INDIControl.py:129) / 0.5 (INDIControl_6DOF.py:234) */
   double init_thrust;                   /* 0.0 (INDIControl.py:127) / 0.3 (INDIControl_6DOF.py:232) */
+  double max_speed_kmh;                 /* MAX_SPEED_KMH (BaseAviary.py:2079): SPEED_LIMIT of VelocityAviary.py:92-94 */
 } ds_type_params;
 
 /* Where the controller's set-points come from. */
 typedef struct ds_targets {
-  int32_t mode;          /* 0: per-vehicle device arrays; 1: shared waypoint table + per-vehicle counter */
+  int32_t mode;          /* 0: per-vehicle device arrays; 1: shared waypoint table + per-vehicle counter;
+                            2: velocity command (VelocityAviary._preprocessAction, VelocityAviary.py:221-264): `vel`
+                               holds the raw action (x, y, z direction, fraction of the speed limit); the target
+                               position / yaw are the vehicle's own, target_vel = SPEED_LIMIT |a3| unit(a012) */
   int32_t num_wp;        /* mode 1: rows in table */
   int32_t advance_wp;    /* mode 1: wp = wp+1 if wp < num_wp-1 else 0 after each control step (fly_INDI.py:242-245) */
   int32_t reserved;
   const float* pos_yaw;  /* mode 0: DEVICE [N][4] = target x,y,z,yaw */
-  const float* vel;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros */
+  const float* vel;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros; mode 2: DEVICE [N][4] velocity action */
   const float* acc;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros */
   const float* table;    /* mode 1: DEVICE [num_wp][12] = pos xyz,yaw | vel xyz,0 | acc xyz,0 */
   const float* offset;   /* mode 1: DEVICE [N][4] additive position offset or NULL */

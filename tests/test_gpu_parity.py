@@ -405,4 +405,6 @@ def test_host_entry_points_are_equivalent():
         for a, b in zip(outs[0][:4], o[:4]):
             np.testing.assert_array_equal(a, b)
         assert o[4] == outs[0][4] == T * K
-    assert outs[0][3].any() and not outs[0][3].all()  # the floor predicate fires for the low quads only
+    d = outs[0][3]  # [T, E]: the floor predicate fires as the quads sag through z_min during the start-up transient
+    assert d[-1].any() and not d[0].all()
+    assert (d[1:] >= d[:-1]).all()  # done bits are sticky

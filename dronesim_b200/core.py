@@ -83,7 +83,7 @@ class SwarmCore:
                  ground: bool = False, drag: bool = False, downwash: bool = False, stats: bool = False,
                  freq: float = 240.0, aggregate_phy_steps: int = 1, neighbourhood_radius: float = math.inf,
                  gravity: float = 9.8, goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0,
-                 device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None):
+                 device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None, dw_ordered_pairs: bool = False):
         lib = L.lib()
         self.vehicle_types: List[VehicleType] = [m if isinstance(m, VehicleType) else load_vehicle(m, assets_dir)
                                                  for m in slot_models]
@@ -101,7 +101,8 @@ class SwarmCore:
         cfg.n_envs, cfg.drones_per_env, cfg.substeps = self.E, self.D, self.K
         cfg.integrator = L.DS_INTEG_RPY if integrator == "rpy" else L.DS_INTEG_QUAT
         cfg.flags = ((L.DS_FLAG_GROUND if ground else 0) | (L.DS_FLAG_DRAG if drag else 0)
-                     | (L.DS_FLAG_DOWNWASH if downwash else 0) | (L.DS_FLAG_STATS if stats else 0))
+                     | (L.DS_FLAG_DOWNWASH if downwash else 0) | (L.DS_FLAG_STATS if stats else 0)
+                     | (L.DS_FLAG_DW_ORDERED_PAIRS if dw_ordered_pairs else 0))
         cfg.device, cfg.sim_freq, cfg.gravity = self.device_index, float(freq), float(gravity)
         cfg.neighbourhood_radius = float(neighbourhood_radius)
         if goal is not None:

@@ -17,6 +17,7 @@ struct ds_handle {
   int n_types = 0;
   bool types_set = false, is_reset = false;
   bool nu6 = false;
+  bool dw_uniform = true;             // every type shares DW_COEFF_2 / DW_COEFF_3 (symmetric downwash pairs allowed)
   bool first_action_pending = false;  // s_a holds the caller's initial action (fly_INDI.py:214)
   bool act_valid = false;             // s_a holds the last clipped external action (facade path)
   int sm_count = 0;
@@ -217,6 +218,8 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     }
     d.rpm0_sum = (float)rpm0;
     if (p.n_u > 4) h->nu6 = true;
+    if (t == 0) h->dw_uniform = true;
+    else if (d.dw_k2 != dev[0].dw_k2 || d.dw_k3 != dev[0].dw_k3) h->dw_uniform = false;
     DsWlsDev& w = wls[t];
     w.n_u = p.n_u; w.n_v = p.n_v; w.gamma = p.wls_gamma;
     for (int i = 0; i < p.n_v; ++i) {
@@ -336,26 +339,28 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
   return DS_OK;
 }
 
-template <int INTEG, bool DW, bool NU6, int MODE>
+template <int INTEG, int DW, bool NU6, int MODE>
 static void launch_step2(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
   const int grid = grid_for(h, a.n_tiles, DS_MIN_CTAS);
   // warp-level sync of the downwash snapshot needs every env inside one warp: D | 32
-  if (32 % a.D == 0) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
-  else ds_step_kernel<INTEG, DW, NU6, false, MODE><<<grid, DS_TILE, 0, st>>>(a);
+  if (DW == 2 || 32 % a.D == 0) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
+  else if (DW != 2) ds_step_kernel<INTEG, (DW == 2 ? 1 : DW), NU6, false, MODE><<<grid, DS_TILE, 0, st>>>(a);
 }
 template <int MODE>
 static void launch_step(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
-  const bool dw = (a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1;
+  // downwash variant: 0 off, 1 every ordered pair, 2 symmetric pairs (16 drones per env, one Gaussian width for all types)
+  int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
+  if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;
   const bool rpy = h->cfg.integrator == DS_INTEG_RPY;
   const bool nu6 = h->nu6;
-#define DS_CASE(I, W, N) launch_step2<I, W, N, MODE>(h, a, st)
-  if (!rpy) {
-    if (dw) { if (nu6) DS_CASE(0, true, true); else DS_CASE(0, true, false); }
-    else    { if (nu6) DS_CASE(0, false, true); else DS_CASE(0, false, false); }
-  } else {
-    if (dw) { if (nu6) DS_CASE(1, true, true); else DS_CASE(1, true, false); }
-    else    { if (nu6) DS_CASE(1, false, true); else DS_CASE(1, false, false); }
-  }
+#define DS_CASE(I, N)                                       \
+  do {                                                      \
+    if (dw == 2) launch_step2<I, 2, N, MODE>(h, a, st);     \
+    else if (dw == 1) launch_step2<I, 1, N, MODE>(h, a, st); \
+    else launch_step2<I, 0, N, MODE>(h, a, st);             \
+  } while (0)
+  if (!rpy) { if (nu6) DS_CASE(0, true); else DS_CASE(0, false); }
+  else      { if (nu6) DS_CASE(1, true); else DS_CASE(1, false); }
 #undef DS_CASE
 }
 

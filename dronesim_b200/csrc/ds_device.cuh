@@ -16,6 +16,7 @@
 #endif
 #define DS_MAX_TYPES_DEV 8
 #define DS_DW_ROWS (DS_TILE + DS_TILE / 2)       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2
+#define DS_DW_BUF (2 * DS_TILE)                  // rows reserved per snapshot buffer: the symmetric D = 16 variant stores every row twice (DS_TILE / 16 envs x 32 rows)
 
 struct __align__(16) DsRotorDev {
   float ax, ay, az, scale;   // thrust axis (body)            | PWM2RPM_SCALE

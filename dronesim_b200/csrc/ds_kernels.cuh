@@ -129,11 +129,11 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsT
   return t;
 }
 
-template <int INTEG, bool DW, bool NU6, bool WARPSYNC, int MODE>
+template <int INTEG, int DW, bool NU6, bool WARPSYNC, int MODE>
 __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsArgs a) {
   __shared__ __align__(16) DsTypeDev sh_types[DS_MAX_TYPES_DEV];
   __shared__ uint8_t sh_slot_type[32];
-  __shared__ __align__(16) float4 sh_pos[DW ? 2 * DS_DW_ROWS : 1];
+  __shared__ __align__(16) float4 sh_pos[DW ? 2 * DS_DW_BUF : 1];
   __shared__ float sh_stat[ST_COUNT * DS_TILE];
   ds_load_types(a, sh_types);
   if (threadIdx.x < 32) sh_slot_type[threadIdx.x] = (threadIdx.x < a.D) ? a.slot_type[threadIdx.x] : 0;
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
   const bool lane_ok = tid < a.tile_v;
   const int lv = lane_ok ? tid : 0;  // idle lanes shadow local vehicle 0 (no stores) so barriers stay uniform
   const int slot = lv % a.D;
-  const int env_row0 = (lv / a.D) * (a.D + DS_DW_PAD);  // padded row of the env's slot 0 in the downwash snapshot
+  // row of the env's slot 0 in the downwash snapshot: D + 1 padded rows per env, or a 32-row block (symmetric variant)
+  const int env_row0 = (DW == 2) ? (lv / 16) * DS_DW_SYM_ROWS : (lv / a.D) * (a.D + DS_DW_PAD);
   const int my_row = env_row0 + slot;
   const int type_id = sh_slot_type[slot];
   const DsTypeDev& tp = sh_types[type_id];

@@ -100,9 +100,59 @@ __device__ __forceinline__ float ds_downwash_sum(const float4* __restrict__ row,
   return acc;
 }
 
+// ---- symmetric variant (D == 16, every type shares DW_COEFF_2 / DW_COEFF_3 - true of all shipped URDFs) ----------
+// Only the LOWER vehicle of a pair feels the pair's downwash (dz > 0 gate), and the pair term depends on the two
+// positions and (k2, k3) alone, so each of the 120 unordered pairs of an env is evaluated ONCE: in round r = 1..7
+// slot s evaluates the pair (s, s + r mod 16), keeps the term if it is the lower one, otherwise hands it to the
+// partner by a 16-lane-wide SHFL.IDX; round 8 pairs (s, s + 8) are evaluated from both sides and kept locally.
+// 7 x 22 + 17 issued instructions and 24 MUFU per substep instead of 16 x 19 and 48.  The env's snapshot rows are
+// stored twice (rows s and s + 16 of a 32-row block) so the partner row s + r needs no wrap-around arithmetic.
+#define DS_DW_SYM_ROWS 32
+template <bool SEND>
+__device__ __forceinline__ float ds_downwash_pair_sym(float& acc, const float4 o, float px, float py, float pz, float k2,
+                                                      float k3) {
+  const float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
+  const float d2 = fmaf(dy, dy, dx * dx);
+  const float ib = ds_rcp(fmaf(k2, fabsf(dz), k3));  // 1 / beta' of the lower vehicle (its dz is |dz|)
+  const float idz2 = ds_rcp(dz * dz);
+  const float w = idz2 * ds_ex2((ib * ib) * -d2);
+  float theirs = 0.f;
+  if (SEND) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f32 q, %3, 0f42C80000;\n\t"          // dxy^2 < 100
+        "setp.gt.and.f32 p, %2, 0f00000000, q;\n\t"   // partner above me: the term is mine
+        "@p add.f32 %0, %0, %4;\n\t"
+        "setp.lt.and.f32 p, %2, 0f00000000, q;\n\t"   // partner below me: the term is the partner's
+        "selp.f32 %1, %4, 0f00000000, p;\n\t}"
+        : "+f"(acc), "=f"(theirs)
+        : "f"(dz), "f"(d2), "f"(w));
+  } else {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, 0f00000000;\n\t"
+        "setp.lt.and.f32 p, %2, 0f42C80000, p;\n\t"
+        "@p add.f32 %0, %0, %3;\n\t}"
+        : "+f"(acc)
+        : "f"(dz), "f"(d2), "f"(w));
+  }
+  return theirs;
+}
+
+// row: this thread's own row (slot) in the env's 32-row block; slot16 = slot + 16
+__device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict__ row, int slot16, float px, float py,
+                                                       float pz, float k2, float k3) {
+  float acc = 0.f, recv = 0.f;
+#pragma unroll
+  for (int r = 1; r <= 7; ++r) {
+    const float theirs = ds_downwash_pair_sym<true>(acc, row[r], px, py, pz, k2, k3);
+    recv += __shfl_sync(0xffffffffu, theirs, slot16 - r, 16);  // from slot - r (mod 16) of my env
+  }
+  ds_downwash_pair_sym<false>(acc, row[8], px, py, pz, k2, k3);
+  return acc + recv;
+}
+
 // act[] must already be clipped.  prev_rpm_sum: in = sum of rpm of the previously applied action
 // (BaseAviary.py:532), out = sum of rpm of this action.
-template <int INTEG, bool DW, bool NU6, bool WARPSYNC>
+template <int INTEG, int DW, bool NU6, bool WARPSYNC>
 __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_row0, int my_row, float4* sh_pos,
                                            const float* act, PhysState& s, float& prev_rpm_sum) {
   constexpr int NU = NU6 ? 6 : 4;
@@ -196,10 +246,21 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
         py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
         pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
       }
-      float4* buf = sh_pos + (k & 1) * DS_DW_ROWS;
-      buf[my_row] = make_float4(px, py, pz, 0.f);
-      if (WARPSYNC) __syncwarp(); else __syncthreads();
-      const float fz = -tp.dw_k1 * ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
+      float dsum;
+      if (DW == 2) {  // symmetric pairs: env_row0 / my_row index 32-row blocks, slot = my_row - env_row0
+        float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
+        const float4 me = make_float4(px, py, pz, 0.f);
+        buf[my_row] = me;
+        if (my_row - env_row0 < 8) buf[my_row + 16] = me;
+        __syncwarp();
+        dsum = ds_downwash_sum_sym16(buf + my_row, my_row - env_row0 + 16, px, py, pz, tp.dw_k2, tp.dw_k3);
+      } else {
+        float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
+        buf[my_row] = make_float4(px, py, pz, 0.f);
+        if (WARPSYNC) __syncwarp(); else __syncthreads();
+        dsum = ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
+      }
+      const float fz = -tp.dw_k1 * dsum;
       Fz += fz;
       if (has_rc) { tx += -rcy * fz; ty += rcx * fz; }
     }

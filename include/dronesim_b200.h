@@ -48,7 +48,10 @@ enum { DS_INTEG_QUAT = 0, DS_INTEG_RPY = 1 };
 
 /* aerodynamic add-ons = the Physics enum of the reference (BaseAviary.py:41-49):
  * pyb_gnd -> GROUND, pyb_drag -> DRAG, pyb_dw -> DOWNWASH, pyb_gnd_drag_dw -> all three. */
-enum { DS_FLAG_GROUND = 1u, DS_FLAG_DRAG = 2u, DS_FLAG_DOWNWASH = 4u, DS_FLAG_STATS = 8u };
+enum { DS_FLAG_GROUND = 1u, DS_FLAG_DRAG = 2u, DS_FLAG_DOWNWASH = 4u, DS_FLAG_STATS = 8u,
+       /* diagnostics: evaluate every ORDERED downwash pair even where the symmetric kernel variant applies
+        * (16 drones per env, all types sharing dw_coeff_2 / dw_coeff_3); results agree to FP32 summation order */
+       DS_FLAG_DW_ORDERED_PAIRS = 16u };
 
 /* control laws: which reference controller class flies the type */
 enum { DS_LAW_QUAD = 0 /* INDIControl.py */, DS_LAW_6DOF = 1 /* INDIControl_6DOF.py */ };

@@ -103,25 +103,50 @@ SYMBOLS = {
     "ds_launch_count": (C.c_int64, [_H]),
 }
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# translation units: the C ABI + small kernels, and the step kernel's instantiations split by (integrator, mode, rotors)
+_UNITS = [("ds_api.cu", "api", [])] + [
+    ("ds_step_inst.cu", "step_%s%d_%d" % ("qr"[i], m, n), ["-DDS_INST_INTEG=%d" % i, "-DDS_INST_MODE=%d" % m, "-DDS_INST_NU6=%d" % n])
+    for i in (0, 1) for m in (0, 1) for n in (0, 1)]
 
 
-def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: str = None) -> str:
-    """Compile ``csrc/ds_api.cu`` (which includes every kernel header) for sm_100a, in-tree."""
+def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: str = None, only_units=None) -> str:
+    """Compile the CUDA core for sm_100a, in-tree: ``nvcc -c`` of every translation unit in parallel
+    (objects under ``csrc/build/``), then one ``nvcc -shared`` link."""
+    from concurrent.futures import ThreadPoolExecutor
+
     out_path = out_path or LIB_PATH
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "dronesim_b200.h")]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(INCLUDE, "dronesim_b200.h"))
     if not force and os.path.isfile(out_path) and all(os.path.getmtime(out_path) >= os.path.getmtime(s) for s in srcs):
         return out_path
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = ([nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
-           + ["-o", out_path, os.path.join(CSRC, "ds_api.cu")])
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    tag = os.path.basename(out_path).replace("libdronesim_b200", "").replace(".so", "").strip(".") or "main"
+    objdir = os.path.join(CSRC, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_unit(unit):
+        src, name, defs = unit
+        obj = os.path.join(objdir, name + ".o")
+        cmd = ([nvcc] + NVCC_FLAGS + list(extra_flags) + defs + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", "-o", obj, os.path.join(CSRC, src)])
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    units = [u for u in _UNITS if only_units is None or u[1] in only_units]
+    with ThreadPoolExecutor(max_workers=len(units)) as ex:
+        results = list(ex.map(compile_unit, units))
+    for obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed building %s" % obj)
+        if verbose:
+            sys.stderr.write(res.stderr)
+    objs = [os.path.join(objdir, u[1] + ".o") for u in _UNITS]
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libdronesim_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc failed linking libdronesim_b200.so")
     return out_path
 
 

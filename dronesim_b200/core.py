@@ -199,6 +199,15 @@ class SwarmCore:
         t._keep = (v,)
         return t
 
+    def targets_rate_thrust(self, rate_thrust) -> L.ds_targets:
+        """mode 3: ``rate_thrust`` [N,4] = RPYTAviary actions (p, q, r set-point, thrust); quad-law types only."""
+        t = L.ds_targets()
+        v = self._dev4(rate_thrust, "rate_thrust")
+        t.mode = 3
+        t.vel = v.data_ptr()
+        t._keep = (v,)
+        return t
+
     def targets_table(self, table, offset=None, advance: bool = True) -> L.ds_targets:
         """mode 1: ``table`` [num_wp, 10] = pos3, vel3, acc3, yaw (the layout of the reference examples'
         TARGET_POS/VEL/ACC/RPYS rows), shared by all vehicles; per-vehicle counters live in the state."""

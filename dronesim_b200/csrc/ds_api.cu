@@ -9,7 +9,8 @@
 #include <vector>
 
 #include "../../include/dronesim_b200.h"
-#include "ds_kernels.cuh"
+#include "ds_aux_kernels.cuh"
+#include "ds_step_inst.cuh"
 
 struct ds_handle {
   ds_config cfg;
@@ -17,6 +18,7 @@ struct ds_handle {
   int n_types = 0;
   bool types_set = false, is_reset = false;
   bool nu6 = false;
+  bool any_6dof = false;              // some type flies the 6-DOF law (no rate / thrust entry: INDIControl_6DOF has none)
   bool dw_uniform = true;             // every type shares DW_COEFF_2 / DW_COEFF_3 (symmetric downwash pairs allowed)
   bool first_action_pending = false;  // s_a holds the caller's initial action (fly_INDI.py:214)
   bool act_valid = false;             // s_a holds the last clipped external action (facade path)
@@ -182,7 +184,7 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
                           h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[2]};
     for (int i = 0; i < 9; ++i) { d.J[i] = (float)p.J[i]; d.Jinv[i] = (float)Ji[i]; }
     for (int i = 0; i < 3; ++i) d.rc[i] = (float)rc[i];
-    d.has_rc = (rc[0] != 0.0 || rc[1] != 0.0 || rc[2] != 0.0) ? 1 : 0;
+    d.has_rc = (rc[0] != 0.0 || rc[1] != 0.0) ? 1 : (rc[2] != 0.0 ? 2 : 0);  // general | along body z only | none
     d.inv_mass = (float)(1.0 / p.mass);
     d.kf = (float)p.kf;
     d.gnd_k = (float)(p.gnd_eff_coeff * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
@@ -218,6 +220,8 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     }
     d.rpm0_sum = (float)rpm0;
     if (p.n_u > 4) h->nu6 = true;
+    if (t == 0) h->any_6dof = false;
+    if (p.law == DS_LAW_6DOF) h->any_6dof = true;
     if (t == 0) h->dw_uniform = true;
     else if (d.dw_k2 != dev[0].dw_k2 || d.dw_k3 != dev[0].dw_k3) h->dw_uniform = false;
     DsWlsDev& w = wls[t];
@@ -333,35 +337,24 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
   } else if (t->mode == 2) {
     if (!t->vel) return DS_ERR_INVALID;
     a.t_vel = (const float4*)t->vel;
+  } else if (t->mode == 3) {
+    if (!t->vel) return DS_ERR_INVALID;
+    a.rate_thrust = (const float4*)t->vel;
   } else {
     return DS_ERR_INVALID;
   }
   return DS_OK;
 }
 
-template <int INTEG, int DW, bool NU6, int MODE>
-static void launch_step2(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
-  const int grid = grid_for(h, a.n_tiles, DS_MIN_CTAS);
-  // warp-level sync of the downwash snapshot needs every env inside one warp: D | 32
-  if (DW == 2 || 32 % a.D == 0) ds_step_kernel<INTEG, DW, NU6, true, MODE><<<grid, DS_TILE, 0, st>>>(a);
-  else if (DW != 2) ds_step_kernel<INTEG, (DW == 2 ? 1 : DW), NU6, false, MODE><<<grid, DS_TILE, 0, st>>>(a);
-}
+// The step-kernel instantiations live in ds_step_inst.cu, compiled once per (integrator, mode) pair so that the
+// translation units build in parallel; see ds_step_inst.cuh for the dispatcher.
 template <int MODE>
 static void launch_step(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
   // downwash variant: 0 off, 1 every ordered pair, 2 symmetric pairs (16 drones per env, one Gaussian width for all types)
   int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
   if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;
-  const bool rpy = h->cfg.integrator == DS_INTEG_RPY;
-  const bool nu6 = h->nu6;
-#define DS_CASE(I, N)                                       \
-  do {                                                      \
-    if (dw == 2) launch_step2<I, 2, N, MODE>(h, a, st);     \
-    else if (dw == 1) launch_step2<I, 1, N, MODE>(h, a, st); \
-    else launch_step2<I, 0, N, MODE>(h, a, st);             \
-  } while (0)
-  if (!rpy) { if (nu6) DS_CASE(0, true); else DS_CASE(0, false); }
-  else      { if (nu6) DS_CASE(1, true); else DS_CASE(1, false); }
-#undef DS_CASE
+  const int grid = grid_for(h, a.n_tiles, DS_MIN_CTAS);
+  ds_launch_step(h->cfg.integrator == DS_INTEG_RPY ? 1 : 0, MODE, dw, h->nu6, 32 % a.D == 0, a, grid, st);
 }
 
 static void time_flags(const ds_handle* h, DsArgs& a) {
@@ -376,6 +369,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   base_args(h, a);
   int rc = set_targets(a, tgt);
   if (rc != DS_OK) return rc;
+  if (a.tmode == 3 && h->any_6dof) return DS_ERR_UNSUPPORTED;  // _INDIRateControl exists for the quad law only
   a.order = order;
   a.ctrl_dt = (float)h->cfg.substeps / h->cfg.sim_freq;  // CTRL_EVERY_N_STEPS * env.TIMESTEP (fly_INDI.py:231)
   a.inv_ctrl_dt = h->cfg.sim_freq / (float)h->cfg.substeps;
@@ -454,6 +448,7 @@ extern "C" int ds_control_from_state(ds_handle* h, const float* state, const ds_
 extern "C" int ds_rate_control_step(ds_handle* h, const float* rate_thrust, float control_timestep, float* cmd_out,
                                     void* stream) {
   if (!rate_thrust) return DS_ERR_INVALID;
+  if (h && h->any_6dof) return DS_ERR_UNSUPPORTED;  // _INDIRateControl exists for the quad law only
   return control_common(h, nullptr, nullptr, rate_thrust, control_timestep, cmd_out, nullptr, nullptr, stream);
 }
 

@@ -44,7 +44,7 @@ struct __align__(16) DsTypeDev {
   int n_u;
   int law;
   float rpm0_sum;            // sum_i PWM2RPM_CONST_i  (rpm of the all-zero action, BaseAviary.py:659-662)
-  int has_rc;                // centre of mass is not the base-frame origin (and the integrator is QUAT)
+  int has_rc;                // centre of mass vs base-frame origin (QUAT integrator): 0 same point, 1 general offset, 2 offset along body z only
   float speed_limit;         // MAX_SPEED_KMH * 1000 / 3600 (VelocityAviary.py:92-94)
   float pad_[23];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
 };

@@ -152,17 +152,21 @@ __device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict_
 
 // act[] must already be clipped.  prev_rpm_sum: in = sum of rpm of the previously applied action
 // (BaseAviary.py:532), out = sum of rpm of this action.
-template <int INTEG, int DW, bool NU6, bool WARPSYNC>
+// FX >= 0: ground effect (bit 0) / drag (bit 1) resolved at compile time; FX < 0: run-time a.flags.
+// Centre-of-mass offset rc (QUAT integrator only; tp.has_rc: 0 none, 1 general, 2 along body z only - the shipped
+// hexa): the state is integrated at the centre of mass, the add-ons that the reference applies at the base-frame
+// origin (drag, downwash: R7 of oracle/dynamics.py) see p_base = c - R rc, v_base = u - R (w x rc) and add the
+// torque (-rc) x f.
+template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX>
 __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_row0, int my_row, float4* sh_pos,
                                            const float* act, PhysState& s, float& prev_rpm_sum) {
   constexpr int NU = NU6 ? 6 : 4;
   const float dt = a.dt;
-#ifdef DS_EXP_FX  // experiment: flags as compile-time constants (straight-line substep body)
-  constexpr bool gnd = true, drag = true;
-#else
-  const bool gnd = (a.flags & 1u) != 0, drag = (a.flags & 2u) != 0;
-#endif
-  const bool has_rc = (INTEG == 0) && (tp.has_rc != 0);  // per type (quads of the shipped URDFs have none)
+  const bool gnd = (FX >= 0) ? ((FX & 1) != 0) : ((a.flags & 1u) != 0);
+  const bool drag = (FX >= 0) ? ((FX & 2) != 0) : ((a.flags & 2u) != 0);
+  const int rc_kind = (INTEG == 0) ? tp.has_rc : 0;  // per type (quads of the shipped URDFs have none)
+  const bool has_rc = rc_kind != 0;
+  const bool rc_gen = rc_kind == 1;
 
   // ---- per control step: rotor thrusts and the constant part of the body wrench
   float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
@@ -182,54 +186,91 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
   if (INTEG == 1) ds_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);  // state cache rpy (BaseAviary.py:729)
 
+  // R rc and R (w x rc) for the current attitude / rates
+  auto rot_rc = [&](const Mat3& R, float& ox, float& oy, float& oz) {
+    ox = R.m02 * rcz; oy = R.m12 * rcz; oz = R.m22 * rcz;
+    if (rc_gen) {
+      ox += R.m00 * rcx + R.m01 * rcy; oy += R.m10 * rcx + R.m11 * rcy; oz += R.m20 * rcx + R.m21 * rcy;
+    }
+  };
+  auto rot_wxrc = [&](const Mat3& R, float& ox, float& oy, float& oz) {
+    float kx = s.wy * rcz, ky = -s.wx * rcz;  // w x rc, rc along z
+    if (rc_gen) {
+      kx -= s.wz * rcy; ky += s.wz * rcx;
+      const float kz = s.wx * rcy - s.wy * rcx;
+      ox = R.m00 * kx + R.m01 * ky + R.m02 * kz; oy = R.m10 * kx + R.m11 * ky + R.m12 * kz;
+      oz = R.m20 * kx + R.m21 * ky + R.m22 * kz;
+    } else {
+      ox = R.m00 * kx + R.m01 * ky; oy = R.m10 * kx + R.m11 * ky; oz = R.m20 * kx + R.m21 * ky;
+    }
+  };
+
   // QUAT: integrate centre-of-mass position / velocity
   float cx = s.px, cy = s.py, cz = s.pz, ux = s.vx, uy = s.vy, uz = s.vz;
   if (has_rc) {
-    Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    cx += R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
-    cy += R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
-    cz += R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
-    float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
-    ux += R.m00 * kx + R.m01 * ky + R.m02 * kz;
-    uy += R.m10 * kx + R.m11 * ky + R.m12 * kz;
-    uz += R.m20 * kx + R.m21 * ky + R.m22 * kz;
+    const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+    float ox, oy, oz;
+    rot_rc(R, ox, oy, oz);
+    cx += ox; cy += oy; cz += oz;
+    rot_wxrc(R, ox, oy, oz);
+    ux += ox; uy += oy; uz += oz;
   }
   // drag coefficient x rotor speed sum: the first substep still sees the previously applied action (:532,:545)
   const float dk0 = -tp.drag_k[0], dk1 = -tp.drag_k[1], dk2 = -tp.drag_k[2];
 
   for (int k = 0; k < a.K; ++k) {
+    // ---- downwash first (BaseAviary.py:1747-1763): it needs the base-frame origin only, so the rotation matrix
+    // does not have to stay live (or be rematerialised) across the unrolled pair loop
+    float dw_fz = 0.f;
+    if (DW) {  // every drone of the env reads the same position snapshot
+      float px = cx, py = cy, pz = cz;  // base-frame origin
+      if (has_rc) {
+        const Mat3 Rp = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+        float ox, oy, oz;
+        rot_rc(Rp, ox, oy, oz);
+        px -= ox; py -= oy; pz -= oz;
+      }
+      float dsum;
+      float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
+      if (DW == 2) {  // symmetric pairs: env_row0 / my_row index 32-row blocks, slot = my_row - env_row0
+        const float4 me = make_float4(px, py, pz, 0.f);
+        buf[my_row] = me;
+        if (my_row - env_row0 < 8) buf[my_row + 16] = me;
+        __syncwarp();
+        dsum = ds_downwash_sum_sym16(buf + my_row, my_row - env_row0 + 16, px, py, pz, tp.dw_k2, tp.dw_k3);
+      } else {
+        buf[my_row] = make_float4(px, py, pz, 0.f);
+        if (WARPSYNC) __syncwarp(); else __syncthreads();
+        dsum = ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
+      }
+      dw_fz = -tp.dw_k1 * dsum;
+    }
+
     const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    float Fx = F0x, Fy = F0y, Fz = F0z, tx = t0x, ty = t0y, tz = t0z;
+    float Fx = F0x, Fy = F0y, Fz = F0z + dw_fz, tx = t0x, ty = t0y, tz = t0z;
+    if (DW && rc_gen) { tx += -rcy * dw_fz; ty += rcx * dw_fz; }  // (-rc) x (0, 0, f)
 
     if (gnd) {  // BaseAviary.py:1672-1699; rotor sites are stored relative to the centre of mass
       bool gate;
       if (INTEG == 1) gate = (fabsf(roll) < 0.5f * DS_PI_F) && (fabsf(pitch) < 0.5f * DS_PI_F);
       else gate = (R.m22 > 0.f) && (fabsf(R.m20) < DS_GIMBAL);  // |roll| < pi/2 <=> cos(roll)cos(pitch) > 0
-#ifdef DS_EXP_FX
-      const float gsel = gate ? 1.f : 0.f;
-      {
-#else
-      const float gsel = 1.f;
-      if (gate) {
-#endif
+      const float gsel = gate ? 1.f : 0.f;  // branch-free: the gate is false only for an inverted vehicle
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          const DsRotorDev& r = tp.rotor[i];
-          float h = fmaf(R.m20, r.rx, fmaf(R.m21, r.ry, fmaf(R.m22, r.rz, cz)));
-          float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
-          float g = (Tg[i] * ih) * (ih * gsel);
-          Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
-          tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
-        }
+      for (int i = 0; i < NU; ++i) {
+        const DsRotorDev& r = tp.rotor[i];
+        float h = fmaf(R.m20, r.rx, fmaf(R.m21, r.ry, fmaf(R.m22, r.rz, cz)));
+        float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
+        float g = (Tg[i] * ih) * (ih * gsel);
+        Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
+        tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
       }
     }
     if (drag) {  // BaseAviary.py:1719-1732
       float vx = ux, vy = uy, vz = uz;
       if (has_rc) {  // velocity of the base origin
-        float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
-        vx -= R.m00 * kx + R.m01 * ky + R.m02 * kz;
-        vy -= R.m10 * kx + R.m11 * ky + R.m12 * kz;
-        vz -= R.m20 * kx + R.m21 * ky + R.m22 * kz;
+        float ox, oy, oz;
+        rot_wxrc(R, ox, oy, oz);
+        vx -= ox; vy -= oy; vz -= oz;
       }
       const float sum = (k == 0) ? prev_rpm_sum : rpm_sum;
       float d0 = (dk0 * sum) * vx, d1 = (dk1 * sum) * vy, d2 = (dk2 * sum) * vz;
@@ -237,32 +278,10 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
       float fy = R.m10 * d0 + R.m11 * d1 + R.m12 * d2;
       float fz = R.m20 * d0 + R.m21 * d1 + R.m22 * d2;
       Fx += fx; Fy += fy; Fz += fz;
-      if (has_rc) { tx += -rcy * fz + rcz * fy; ty += -rcz * fx + rcx * fz; tz += -rcx * fy + rcy * fx; }
-    }
-    if (DW) {  // BaseAviary.py:1747-1763: every drone of the env reads the same position snapshot
-      float px = cx, py = cy, pz = cz;  // base-frame origin
-      if (has_rc) {
-        px -= R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
-        py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
-        pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
+      if (has_rc) {  // (-rc) x f
+        tx = fmaf(rcz, fy, tx); ty = fmaf(-rcz, fx, ty);
+        if (rc_gen) { tx += -rcy * fz; ty += rcx * fz; tz += -rcx * fy + rcy * fx; }
       }
-      float dsum;
-      if (DW == 2) {  // symmetric pairs: env_row0 / my_row index 32-row blocks, slot = my_row - env_row0
-        float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
-        const float4 me = make_float4(px, py, pz, 0.f);
-        buf[my_row] = me;
-        if (my_row - env_row0 < 8) buf[my_row + 16] = me;
-        __syncwarp();
-        dsum = ds_downwash_sum_sym16(buf + my_row, my_row - env_row0 + 16, px, py, pz, tp.dw_k2, tp.dw_k3);
-      } else {
-        float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
-        buf[my_row] = make_float4(px, py, pz, 0.f);
-        if (WARPSYNC) __syncwarp(); else __syncthreads();
-        dsum = ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
-      }
-      const float fz = -tp.dw_k1 * dsum;
-      Fz += fz;
-      if (has_rc) { tx += -rcy * fz; ty += rcx * fz; }
     }
 
     // ---- Newton-Euler (BaseAviary.py:1790-1807)
@@ -296,14 +315,12 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   // back to base-frame origin
   s.px = cx; s.py = cy; s.pz = cz; s.vx = ux; s.vy = uy; s.vz = uz;
   if (has_rc) {
-    Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    s.px -= R.m00 * rcx + R.m01 * rcy + R.m02 * rcz;
-    s.py -= R.m10 * rcx + R.m11 * rcy + R.m12 * rcz;
-    s.pz -= R.m20 * rcx + R.m21 * rcy + R.m22 * rcz;
-    float kx = s.wy * rcz - s.wz * rcy, ky = s.wz * rcx - s.wx * rcz, kz = s.wx * rcy - s.wy * rcx;
-    s.vx -= R.m00 * kx + R.m01 * ky + R.m02 * kz;
-    s.vy -= R.m10 * kx + R.m11 * ky + R.m12 * kz;
-    s.vz -= R.m20 * kx + R.m21 * ky + R.m22 * kz;
+    const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+    float ox, oy, oz;
+    rot_rc(R, ox, oy, oz);
+    s.px -= ox; s.py -= oy; s.pz -= oz;
+    rot_wxrc(R, ox, oy, oz);
+    s.vx -= ox; s.vy -= oy; s.vz -= oz;
   }
   prev_rpm_sum = rpm_sum;
 }

@@ -19,7 +19,7 @@
 #define WLS_INFINITY 1e32      // wls_alloc.py:88
 
 // least squares  min |A x - b|, A is (n_c x n) column-major with leading dimension WLS_NC
-__device__ __noinline__ void ds_lstsq_qr(double* A, double* b, int n_c, int n, double* x) {
+static __device__ __noinline__ void ds_lstsq_qr(double* A, double* b, int n_c, int n, double* x) {
   for (int k = 0; k < n; ++k) {
     double* ak = A + k * WLS_NC;
     double nrm = 0.0;
@@ -57,7 +57,7 @@ __device__ __noinline__ void ds_lstsq_qr(double* A, double* b, int n_c, int n, d
 }
 
 // returns the iteration count, or -iterations on non-convergence (reference returns None, :350)
-__device__ __noinline__ int ds_wls_alloc(const DsWlsDev* __restrict__ P, const double* v, const double* umin,
+static __device__ __noinline__ int ds_wls_alloc(const DsWlsDev* __restrict__ P, const double* v, const double* umin,
                                          const double* umax, double* u_out) {
   const int n_u = P->n_u, n_v = P->n_v, n_c = n_u + n_v;
   double A[WLS_NC * WLS_NU];       // row-major [n_c][6]

@@ -123,12 +123,16 @@ typedef struct ds_targets {
   int32_t mode;          /* 0: per-vehicle device arrays; 1: shared waypoint table + per-vehicle counter;
                             2: velocity command (VelocityAviary._preprocessAction, VelocityAviary.py:221-264): `vel`
                                holds the raw action (x, y, z direction, fraction of the speed limit); the target
-                               position / yaw are the vehicle's own, target_vel = SPEED_LIMIT |a3| unit(a012) */
+                               position / yaw are the vehicle's own, target_vel = SPEED_LIMIT |a3| unit(a012);
+                            3: body-rate + thrust command (RPYTAviary._preprocessAction, RPYTAviary.py:180-193 ->
+                               INDIControl._INDIRateControl, INDIControl.py:413-490): `vel` holds (p, q, r set-point, thrust);
+                               quad-law types only (DS_ERR_UNSUPPORTED otherwise) */
   int32_t num_wp;        /* mode 1: rows in table */
   int32_t advance_wp;    /* mode 1: wp = wp+1 if wp < num_wp-1 else 0 after each control step (fly_INDI.py:242-245) */
   int32_t reserved;
   const float* pos_yaw;  /* mode 0: DEVICE [N][4] = target x,y,z,yaw */
-  const float* vel;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros; mode 2: DEVICE [N][4] velocity action */
+  const float* vel;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros; mode 2: DEVICE [N][4] velocity action;
+                            mode 3: DEVICE [N][4] rate / thrust action */
   const float* acc;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros */
   const float* table;    /* mode 1: DEVICE [num_wp][12] = pos xyz,yaw | vel xyz,0 | acc xyz,0 */
   const float* offset;   /* mode 1: DEVICE [N][4] additive position offset or NULL */

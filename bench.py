@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 50)")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=0, help="control steps of the CPU baseline sample; 0 = sized for ~12 s")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary (single-type) workloads")
     return ap.parse_args()
 
@@ -351,7 +351,8 @@ def run_ours(args):
     bytes_per_launch = hetero16_bytes_per_control_step() * N
     hbm_achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "ds_step_kernel<QUAT,DW,NU6,WARPSYNC,FUSED>",
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "ds_step_kernel<QUAT, DW=symmetric16, NU6, WARPSYNC, FUSED, FX=ground+drag>",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "algorithmic_bytes_per_vehicle_control_step": hetero16_bytes_per_control_step()}
     prof = os.path.join(ROOT, "profiles", "roofline_inputs.json")
@@ -365,8 +366,23 @@ def run_ours(args):
                 if pin.get("dram_bytes_per_launch"):
                     roofline["traffic"] = pin["dram_bytes_per_launch"] * scale
                 if pin.get("fp32_flop_per_launch"):
+                    # algorithmic FLOP: the FP32 operations of the straightforward formulation (every ordered downwash
+                    # pair evaluated, as the reference's double loop does), counted once by ncu on the r1f build
                     fl = pin["fp32_flop_per_launch"] * scale
                     fp32 = {"flop_per_launch": fl, "source": pin.get("source", "profiles/")}
+                    if pin.get("fp32_flop_executed_per_launch"):
+                        fp32["flop_executed_per_launch"] = pin["fp32_flop_executed_per_launch"] * scale
+                if pin.get("warp_inst_per_launch"):
+                    # the limit that actually binds this kernel: warp instructions issued per second against
+                    # SMs x 4 schedulers x SM clock (one instruction per scheduler per cycle)
+                    sm = float(clocks.get("sm_mhz") or 0.0) * 1e6
+                    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                    wi = pin["warp_inst_per_launch"] * scale
+                    if sm > 0:
+                        roofline["issue"] = {"warp_inst_per_launch": wi, "achieved_ginst_s": wi / (ms_per_step * 1e-3) / 1e9,
+                                             "peak_ginst_s": sms * 4 * sm / 1e9,
+                                             "frac": wi / (ms_per_step * 1e-3) / (sms * 4 * sm),
+                                             "source": pin.get("source_inst", pin.get("source", "profiles/"))}
         except Exception:
             pass
     if rank == 0:
@@ -387,7 +403,12 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_bench import time_oracle
 
-        r = time_oracle(steps=args.cpu_steps, warmup=1, workers=os.cpu_count() or 1, envs_per_worker=1)
+        cores = os.cpu_count() or 1
+        n_cpu = args.cpu_steps
+        if n_cpu <= 0:  # bounded sample: ~12 s of CPU work, sized from a 2-step calibration
+            cal = time_oracle(steps=2, warmup=1, workers=cores, envs_per_worker=1)
+            n_cpu = int(min(600, max(3, round(12.0 / max(cal["seconds"] / 2.0, 1e-3)))))
+        r = time_oracle(steps=n_cpu, warmup=1, workers=cores, envs_per_worker=1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "seconds": r["seconds"]}
 

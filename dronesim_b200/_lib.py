@@ -92,6 +92,8 @@ SYMBOLS = {
     "ds_views": (C.c_int, [_H, C.POINTER(ds_state_views)]),
     "ds_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
     "ds_stats_reset": (C.c_int, [_H, C.c_void_p]),
+    "ds_log_attach": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "ds_log_read": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "ds_step_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_rollout_host": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -339,5 +339,22 @@ class SwarmCore:
                                      1 if force_slow else 0, self._stream()), self._h)
         return du, it
 
+    # ------------------------------------------------------------------ trajectory capture (Logger layout)
+    def log_attach(self, vehicles, capacity: int):
+        """Record the state vector of ``vehicles`` (ids ``env * D + slot``) after every control / physics step."""
+        ids = np.ascontiguousarray(np.asarray(vehicles, dtype=np.int32).reshape(-1))
+        self._log_n, self._log_cap = int(ids.shape[0]), int(capacity)
+        L.check(L.lib().ds_log_attach(self._h, ids.ctypes.data_as(C.c_void_p), self._log_n, self._log_cap), self._h)
+
+    def log_read(self):
+        """-> (timestamps [count], states [n_vehicles, 22, count]) as float64 numpy (Logger.timestamps / Logger.states)."""
+        n, cap = getattr(self, "_log_n", 0), getattr(self, "_log_cap", 0)
+        states = np.zeros((n, L.DS_OBS_STRIDE, cap), dtype=np.float32)
+        ts = np.zeros((max(cap, 1),), dtype=np.float64)
+        cnt = C.c_int32(0)
+        L.check(L.lib().ds_log_read(self._h, states.ctypes.data_as(C.c_void_p) if n else None,
+                                    ts.ctypes.data_as(C.c_void_p), C.byref(cnt), self._stream()), self._h)
+        return ts[: cnt.value].copy(), states[:, :, : cnt.value].astype(np.float64)
+
     def launch_count(self) -> int:
         return int(L.lib().ds_launch_count(self._h))

@@ -46,6 +46,11 @@ struct ds_handle {
   uint8_t* d_roll_done[2] = {nullptr, nullptr};
   cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
+  // trajectory capture (ds_log_*): Logger-layout samples of selected vehicles
+  int32_t* d_log_ids = nullptr;
+  float* d_log_states = nullptr;
+  int log_n = 0, log_cap = 0, log_count = 0;
+  std::vector<double> log_time;
   uint8_t slot_type[DS_MAX_DRONES_PER_ENV];
 };
 
@@ -76,7 +81,7 @@ static void free_all(ds_handle* h) {
   void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
                   h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
-                  h->d_roll_done[1]};
+                  h->d_roll_done[1], h->d_log_ids, h->d_log_states};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; ++b) {
@@ -302,8 +307,10 @@ extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, cons
   }
   CK(cudaStreamSynchronize(st));  // the host arrays may be freed by the caller after return
   h->step_counter = 0;
+  h->log_count = 0;
+  h->log_time.clear();
   h->first_action_pending = (action0 != nullptr);
-  h->act_valid = false;
+  h->act_valid = (action0 == nullptr);  // obs tail after reset = last_clipped_action = zeros (BaseAviary.py:659-662)
   h->is_reset = true;
   return DS_OK;
 }
@@ -357,6 +364,8 @@ static void launch_step(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
   ds_launch_step(h->cfg.integrator == DS_INTEG_RPY ? 1 : 0, MODE, dw, h->nu6, 32 % a.D == 0, a, grid, st);
 }
 
+static int log_sample(ds_handle* h, cudaStream_t st);
+
 static void time_flags(const ds_handle* h, DsArgs& a) {
   a.time_hit = (h->cfg.max_steps > 0 && h->step_counter + h->cfg.substeps >= h->cfg.max_steps) ? 1 : 0;
 }
@@ -383,6 +392,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
     h->first_action_pending = false;
     h->act_valid = false;
     h->step_counter += h->cfg.substeps;  // BaseAviary.py:554
+    log_sample(h, st);
   }
   CK(cudaGetLastError());
   return DS_OK;
@@ -403,6 +413,8 @@ extern "C" int ds_physics_step(ds_handle* h, const float* action, void* stream) 
   h->first_action_pending = false;
   h->act_valid = true;
   h->step_counter += h->cfg.substeps;
+  log_sample(h, (cudaStream_t)stream);
+  CK(cudaGetLastError());
   return DS_OK;
 }
 
@@ -416,6 +428,10 @@ static int control_common(ds_handle* h, const float* state, const ds_targets* tg
   if (!rate_thrust) {
     int rc = set_targets(a, tgt);
     if (rc != DS_OK) return rc;
+    if (a.tmode == 3) {  // rate / thrust targets (RPYTAviary) on the resident or the caller's state
+      if (h->any_6dof) return DS_ERR_UNSUPPORTED;
+      rate_thrust = (const float*)a.rate_thrust;
+    }
   }
   a.ext_state = state;
   a.rate_thrust = (const float4*)rate_thrust;
@@ -452,21 +468,69 @@ extern "C" int ds_rate_control_step(ds_handle* h, const float* rate_thrust, floa
   return control_common(h, nullptr, nullptr, rate_thrust, control_timestep, cmd_out, nullptr, nullptr, stream);
 }
 
-extern "C" int ds_get_obs(ds_handle* h, float* obs, uint32_t* neighbors, uint8_t* done_env, float* reward_env,
-                          void* stream) {
-  if (!h) return DS_ERR_INVALID;
-  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
-  DsObsArgs a;
+static void obs_args(const ds_handle* h, DsObsArgs& a) {
+  memset(&a, 0, sizeof(a));
   a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv;
   // obs tail = last_clipped_action (BaseAviary.py:787): the external action on the facade path, else the
   // controller command (which is the action the next physics step applies)
   a.s_c0 = h->act_valid ? h->s_a0 : h->s_c0;
   a.s_c1 = h->act_valid ? h->s_a1 : h->s_c1;
   a.slot_type = h->d_slot_type; a.types = h->d_types;
-  a.obs = obs; a.neighbors = neighbors; a.done_env = done_env; a.reward_env = reward_env;
   a.n = h->n; a.D = h->cfg.drones_per_env; a.nu6 = h->nu6 ? 1 : 0;
   a.radius = h->cfg.neighbourhood_radius;
+}
+
+// one Logger sample of the attached vehicles (after a control / physics step); full buffer: samples are dropped
+static int log_sample(ds_handle* h, cudaStream_t st) {
+  if (!h->log_n || h->log_count >= h->log_cap) return DS_OK;
+  DsObsArgs a;
+  obs_args(h, a);
+  ds_log_kernel<<<(h->log_n + 127) / 128, 128, 0, st>>>(a, h->d_log_ids, h->log_n, h->d_log_states, h->log_cap, h->log_count);
+  h->launches++;
+  h->log_time.push_back((double)h->step_counter / (double)h->cfg.sim_freq);
+  h->log_count++;
+  return DS_OK;
+}
+
+extern "C" int ds_log_attach(ds_handle* h, const int32_t* vehicles, int32_t n_vehicles, int32_t capacity) {
+  if (!h || n_vehicles < 0 || capacity < 0 || (n_vehicles > 0 && (!vehicles || capacity == 0))) return DS_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < n_vehicles; ++i)
+    if (vehicles[i] < 0 || vehicles[i] >= h->n) return DS_ERR_INVALID;
+  if (h->d_log_ids) cudaFree(h->d_log_ids);
+  if (h->d_log_states) cudaFree(h->d_log_states);
+  h->d_log_ids = nullptr; h->d_log_states = nullptr;
+  h->log_n = 0; h->log_cap = 0; h->log_count = 0; h->log_time.clear();
+  if (n_vehicles == 0) return DS_OK;
+  CK(cudaMalloc((void**)&h->d_log_ids, sizeof(int32_t) * n_vehicles));
+  CK(cudaMalloc((void**)&h->d_log_states, sizeof(float) * (size_t)n_vehicles * DS_OBS_STRIDE * capacity));
+  CK(cudaMemcpy(h->d_log_ids, vehicles, sizeof(int32_t) * n_vehicles, cudaMemcpyHostToDevice));
+  CK(cudaMemset(h->d_log_states, 0, sizeof(float) * (size_t)n_vehicles * DS_OBS_STRIDE * capacity));
+  h->log_n = n_vehicles; h->log_cap = capacity;
+  return DS_OK;
+}
+
+extern "C" int ds_log_read(ds_handle* h, float* host_states, double* host_timestamps, int32_t* count_out, void* stream) {
+  if (!h || !count_out) return DS_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  *count_out = h->log_count;
+  if (host_states && h->log_n)
+    CK(cudaMemcpyAsync(host_states, h->d_log_states, sizeof(float) * (size_t)h->log_n * DS_OBS_STRIDE * h->log_cap,
+                       cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (host_timestamps)
+    for (int i = 0; i < h->log_count; ++i) host_timestamps[i] = h->log_time[i];
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return DS_OK;
+}
+
+extern "C" int ds_get_obs(ds_handle* h, float* obs, uint32_t* neighbors, uint8_t* done_env, float* reward_env,
+                          void* stream) {
+  if (!h) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  CK(cudaSetDevice(h->cfg.device));
+  DsObsArgs a;
+  obs_args(h, a);
+  a.obs = obs; a.neighbors = neighbors; a.done_env = done_env; a.reward_env = reward_env;
   ds_obs_kernel<<<grid_for(h, (h->n + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(a);
   h->launches++;
   CK(cudaGetLastError());

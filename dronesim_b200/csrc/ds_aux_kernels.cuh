@@ -85,26 +85,34 @@ struct DsObsArgs {
   float radius;
 };
 
+// BaseAviary._getDroneStateVector (BaseAviary.py:780-790) of vehicle v, zero padded to 22 floats
+__device__ __forceinline__ void ds_state_vector(const DsObsArgs& a, int v, float o[22]) {
+  const float4 P = a.s_pos[v], Q = a.s_quat[v], V = a.s_vel[v], W = a.s_om[v], C0 = a.s_c0[v];
+  const float2 C1 = a.nu6 ? a.s_c1[v] : make_float2(0.f, 0.f);
+  float roll, pitch, yaw;
+  ds_euler(Q.x, Q.y, Q.z, Q.w, roll, pitch, yaw);  // BaseAviary.py:729
+  float d = Q.x * Q.x + Q.y * Q.y + Q.z * Q.z + Q.w * Q.w;
+  Mat3 R = ds_rot(Q.x, Q.y, Q.z, Q.w, 2.0f / d);
+  o[0] = P.x; o[1] = P.y; o[2] = P.z;
+  o[3] = Q.x; o[4] = Q.y; o[5] = Q.z; o[6] = Q.w;
+  o[7] = roll; o[8] = pitch; o[9] = yaw;
+  o[10] = V.x; o[11] = V.y; o[12] = V.z;
+  o[13] = R.m00 * W.x + R.m01 * W.y + R.m02 * W.z;  // world angular velocity
+  o[14] = R.m10 * W.x + R.m11 * W.y + R.m12 * W.z;
+  o[15] = R.m20 * W.x + R.m21 * W.y + R.m22 * W.z;
+  o[16] = C0.x; o[17] = C0.y; o[18] = C0.z; o[19] = C0.w; o[20] = C1.x; o[21] = C1.y;
+}
+
 __global__ void __launch_bounds__(256) ds_obs_kernel(const DsObsArgs a) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n; v += gridDim.x * blockDim.x) {
     const int slot = v % a.D, env0 = v - slot;
     float4 P = a.s_pos[v];
     if (a.obs) {
-      float4 Q = a.s_quat[v], V = a.s_vel[v], W = a.s_om[v], C0 = a.s_c0[v];
-      float2 C1 = a.nu6 ? a.s_c1[v] : make_float2(0.f, 0.f);
-      float roll, pitch, yaw;
-      ds_euler(Q.x, Q.y, Q.z, Q.w, roll, pitch, yaw);  // BaseAviary.py:729
-      float d = Q.x * Q.x + Q.y * Q.y + Q.z * Q.z + Q.w * Q.w;
-      Mat3 R = ds_rot(Q.x, Q.y, Q.z, Q.w, 2.0f / d);
-      float* o = a.obs + (size_t)v * 22;  // BaseAviary.py:780-790
-      o[0] = P.x; o[1] = P.y; o[2] = P.z;
-      o[3] = Q.x; o[4] = Q.y; o[5] = Q.z; o[6] = Q.w;
-      o[7] = roll; o[8] = pitch; o[9] = yaw;
-      o[10] = V.x; o[11] = V.y; o[12] = V.z;
-      o[13] = R.m00 * W.x + R.m01 * W.y + R.m02 * W.z;  // world angular velocity
-      o[14] = R.m10 * W.x + R.m11 * W.y + R.m12 * W.z;
-      o[15] = R.m20 * W.x + R.m21 * W.y + R.m22 * W.z;
-      o[16] = C0.x; o[17] = C0.y; o[18] = C0.z; o[19] = C0.w; o[20] = C1.x; o[21] = C1.y;
+      float o[22];
+      ds_state_vector(a, v, o);
+      float* dst = a.obs + (size_t)v * 22;
+#pragma unroll
+      for (int i = 0; i < 22; ++i) dst[i] = o[i];
     }
     if (a.neighbors) {  // BaseAviary._getAdjacencyMatrix (BaseAviary.py:901-921), strict <
       uint32_t bits = 1u << slot;
@@ -127,6 +135,21 @@ __global__ void __launch_bounds__(256) ds_obs_kernel(const DsObsArgs a) {
       if (a.reward_env) a.reward_env[v / a.D] = -1.0f;  // CtrlAviary.py:267-278
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trajectory capture in the reference Logger's layout (dronesim/utils/Logger.py:51-53: states[drone][state][sample]):
+// one thread per logged vehicle writes its state vector into column `col` of a [n_log][22][capacity] array
+// ---------------------------------------------------------------------------------------------
+__global__ void ds_log_kernel(const DsObsArgs a, const int32_t* __restrict__ ids, int n_log, float* __restrict__ states,
+                              int capacity, int col) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_log) return;
+  float o[22];
+  ds_state_vector(a, ids[i], o);
+  float* dst = states + (size_t)i * 22 * capacity + col;
+#pragma unroll
+  for (int k = 0; k < 22; ++k) dst[(size_t)k * capacity] = o[k];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -121,18 +121,19 @@ class BaseAviary:
     def step(self, action):
         """BaseAviary.step (BaseAviary.py:428-555): clip, AGGR_PHY_STEPS substeps with the same action,
         refresh the state cache, return ``obs, reward, done, info``."""
-        import torch
-
-        a = self._pack_action(action)
-        self._core.physics_step(a)
+        self._advance(action)
         self._updateAndStoreKinematicInformation()
         obs = self._computeObs()
         reward = self._computeReward()
         done = self._computeDone()
         info = self._computeInfo()
         self.step_counter = self._core.step_counter  # += AGGR_PHY_STEPS (:554)
-        del torch
         return obs, reward, done, info
+
+    def _advance(self, action):
+        """``_preprocessAction`` + the AGGR_PHY_STEPS substeps (BaseAviary.py:507-545), one kernel launch.
+        CtrlAviary: the action is the PWM command, clipped on the device (CtrlAviary.py:236-263)."""
+        self._core.physics_step(self._pack_action(action))
 
     def render(self, mode="human", close=False):
         """BaseAviary.render (BaseAviary.py:559-620): textual, first env only."""
@@ -180,25 +181,25 @@ class BaseAviary:
         self._core.reset(bc(self.INIT_XYZS), rpy0=bc(self.INIT_RPYS), vel0=vel0)
         self.last_clipped_action = {str(i): np.zeros(self._n_u[i]) for i in range(D)}
 
-    def _pack_action(self, action):
-        """dict {str(i): [n_u_i]} (reference form, one env) or array/tensor [E, D, <=6] -> device [N, 6]."""
+    def _pack_action(self, action, width: int = 6):
+        """dict {str(i): [<= width]} (reference form, one env) or array/tensor [E, D, <= width] -> device [N, width]."""
         import torch
 
         E, D = self.NUM_ENVS, self.NUM_DRONES
         dev = self._core.device
         if isinstance(action, dict):
-            a = np.zeros((D, 6), dtype=np.float32)
+            a = np.zeros((D, width), dtype=np.float32)
             for k, v in action.items():
                 v = np.asarray(v, dtype=np.float32).reshape(-1)
                 a[int(k), : v.shape[0]] = v
             t = torch.from_numpy(a).to(dev)
             if E > 1:
-                t = t.unsqueeze(0).expand(E, D, 6)
-            return t.reshape(E * D, 6).contiguous()
+                t = t.unsqueeze(0).expand(E, D, width)
+            return t.reshape(E * D, width).contiguous()
         t = torch.as_tensor(action, dtype=torch.float32, device=dev)
-        if t.shape[-1] < 6:
-            t = torch.nn.functional.pad(t, (0, 6 - t.shape[-1]))
-        return t.reshape(E * D, 6).contiguous()
+        if t.shape[-1] < width:
+            t = torch.nn.functional.pad(t, (0, width - t.shape[-1]))
+        return t.reshape(E * D, width).contiguous()
 
     def _updateAndStoreKinematicInformation(self):
         """State cache ``pos quat rpy vel ang_v`` (BaseAviary.py:718-732) + clipped action + adjacency,

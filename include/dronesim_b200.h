@@ -202,6 +202,17 @@ int ds_views(ds_handle* h, ds_state_views* out);
 int ds_stats(ds_handle* h, double* host_out, int32_t n, void* stream);
 int ds_stats_reset(ds_handle* h, void* stream);
 
+/* ---- trajectory capture: dronesim/utils/Logger.py on the device --------------------------- */
+/* Logger(logging_freq_hz, num_drones, duration_sec) + Logger.log (Logger.py:22-139): attach `n_vehicles` vehicles
+ * (HOST ids, v = env * drones_per_env + slot); from then on every control step of ds_step and every ds_physics_step
+ * appends one sample - the vehicle's aviary state vector (BaseAviary.py:780-790, what the examples pass to
+ * logger.log) - to a DEVICE array laid out like Logger.states: [n_vehicles][DS_OBS_STRIDE][capacity].  Samples past
+ * `capacity` are dropped; ds_reset rewinds the log; n_vehicles = 0 detaches. */
+int ds_log_attach(ds_handle* h, const int32_t* vehicles, int32_t n_vehicles, int32_t capacity);
+/* Copies the whole array to HOST host_states [n_vehicles][DS_OBS_STRIDE][capacity] (may be NULL) and the sample
+ * times step_counter / SIM_FREQ to HOST host_timestamps [capacity] (may be NULL); *count_out = samples taken. */
+int ds_log_read(ds_handle* h, float* host_states, double* host_timestamps, int32_t* count_out, void* stream);
+
 /* ---- end-to-end convenience with HOST buffers ------------------------------------------ */
 /* One control step driven from the host: copies HOST targets [N][4] (x,y,z,yaw) to the device,
  * runs ds_step, materialises obs and copies obs [N][DS_OBS_STRIDE] + done_env [n_envs] back to

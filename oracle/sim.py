@@ -161,6 +161,47 @@ class OracleSwarm:
         return action
 
 
+    # ------------------------------------------------------------------ controller-embedding aviaries
+    def velocity_preprocess(self, vel_action):
+        """``VelocityAviary._preprocessAction`` (VelocityAviary.py:221-264): ``vel_action[E, D, 4]`` =
+        direction xyz + fraction of the speed limit -> PWM action ``[E, D, 6]``.  ``SPEED_LIMIT`` =
+        ``MAX_SPEED_KMH * 1000 / 3600`` (VelocityAviary.py:92-94).  The reference instantiates the quad-law
+        ``INDIControl`` for every drone; a 6-DOF airframe is flown by its own law here (the reference would
+        fail on the 6x6 ``G1``)."""
+        E, D = self.E, self.D
+        va = np.asarray(vel_action, float).reshape(E, D, 4)
+        dt = self.K * self.TIMESTEP  # control_timestep = AGGR_PHY_STEPS * TIMESTEP (:243)
+        action = np.zeros((E, D, 6))
+        for e in range(E):
+            for d in range(D):
+                state = self.state_vector(e, d)
+                v = va[e, d]
+                n = np.linalg.norm(v[0:3])
+                v_unit = v[0:3] / n if n != 0 else np.zeros(3)  # :239-242
+                speed_limit = self.types[d].MAX_SPEED_KMH * (1000 / 3600)
+                cmd, _, _ = self.ctrl[e][d].computeControl(
+                    control_timestep=dt, cur_pos=state[0:3], cur_quat=state[3:7], cur_vel=state[10:13],
+                    cur_ang_vel=state[13:16], target_pos=state[0:3], target_rpy=np.array([0, 0, state[9]]),
+                    target_vel=speed_limit * np.abs(v[3]) * v_unit)
+                action[e, d, : self.n_u[d]] = cmd
+        return action
+
+    def rate_preprocess(self, rate_thrust):
+        """``RPYTAviary._preprocessAction`` (RPYTAviary.py:180-193): ``rate_thrust[E, D, 4]`` = p, q, r
+        set-point + thrust -> ``INDIControl._INDIRateControl`` (INDIControl.py:413-490) -> PWM action."""
+        E, D = self.E, self.D
+        rt = np.asarray(rate_thrust, float).reshape(E, D, 4)
+        dt = self.K * self.TIMESTEP
+        action = np.zeros((E, D, 6))
+        for e in range(E):
+            for d in range(D):
+                state = self.state_vector(e, d)
+                c = self.ctrl[e][d]
+                c.cmd = c.rate_control(dt, rt[e, d, 3], state[3:7], state[13:16], rt[e, d, 0:3])
+                action[e, d, : self.n_u[d]] = c.cmd
+        return action
+
+
 def next_waypoint(wp, num_wp):
     """fly_INDI.py:242-245."""
     return np.where(wp < num_wp - 1, wp + 1, 0)

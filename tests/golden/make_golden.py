@@ -12,6 +12,8 @@ three PyBullet math functions and an empty gym):
 * dronesim/control/INDIControl_6DOF.py  -> ctrl_hexa_6DOF.npz
 * dronesim/utils/math.py                -> quat_helpers.npz
 * dronesim/utils/trajGen.py             -> traj_3gates.npz (the table of examples/fly_INDI_TrajectoryTrack.py:127-160)
+* dronesim/envs/VelocityAviary.py       -> pre_velocity_<vehicle>.npz (``_preprocessAction`` :221-264, called unbound)
+* dronesim/envs/RPYTAviary.py           -> pre_rpyt_<vehicle>.npz     (``_preprocessAction`` :180-193, called unbound)
 
 The fixtures are small .npz files; they are what travels to the GPU box (the reference does not).
 """
@@ -156,7 +158,50 @@ def traj_fixture():
     return dict(TS=np.array(traj.TS), table=np.array(rows), gates=gates)
 
 
+def preprocess_fixture(kind, name, seed, T=30, n_seq=4):
+    """``VelocityAviary._preprocessAction`` (VelocityAviary.py:221-264) / ``RPYTAviary._preprocessAction``
+    (RPYTAviary.py:180-193) executed UNBOUND on a stand-in ``self`` that carries exactly what the method reads:
+    ``_getDroneStateVector``, ``ctrl`` (a reference INDIControl), ``AGGR_PHY_STEPS``, ``TIMESTEP``, ``SPEED_LIMIT``."""
+    import types
+
+    from dronesim.envs.RPYTAviary import RPYTAviary
+    from dronesim.envs.VelocityAviary import VelocityAviary
+    from dronesim_b200.vehicles import load_vehicle
+
+    rng = np.random.default_rng(seed)
+    vt = load_vehicle(name)
+    method = VelocityAviary._preprocessAction if kind == "velocity" else RPYTAviary._preprocessAction
+    out = dict(states=[], action=[], cmd=[], aggr=[], last_vel=[], last_rates=[], last_thrust=[])
+    for sq in range(n_seq):
+        ctrl = ref_shims.quad_controller(name)
+        aggr = [5, 2, 8, 1][sq % 4]
+        states = rand_state_sequence(rng, 4, T, ang_lim=[0.3, 1.0][sq % 2])
+        seq = {k: [] for k in out}
+        for t in range(T):
+            fake = types.SimpleNamespace(
+                _getDroneStateVector=lambda i, _s=states[t]: _s.copy(), ctrl=[ctrl], AGGR_PHY_STEPS=aggr,
+                TIMESTEP=1.0 / 240, SPEED_LIMIT=[vt.MAX_SPEED_KMH * (1000 / 3600)])
+            if kind == "velocity":
+                a = np.concatenate([rng.normal(0, 1, 3), [rng.uniform(-1, 1)]])
+                if t % 7 == 3:
+                    a[0:3] = 0.0  # the zero-direction branch (:239-242)
+            else:
+                a = np.concatenate([rng.normal(0, 0.5, 3), [rng.uniform(0.0, 1.0)]])  # p, q, r set-point, thrust
+            cmd = np.array(method(fake, {"0": a})["0"], dtype=np.float64)
+            for k, v in (("states", states[t]), ("action", a), ("cmd", cmd), ("aggr", aggr),
+                         ("last_vel", np.array(ctrl.last_vel, float)), ("last_rates", np.array(ctrl.last_rates, float)),
+                         ("last_thrust", float(ctrl.last_thrust))):
+                seq[k].append(np.array(v, dtype=np.float64))
+        for k in out:
+            out[k].append(np.array(seq[k]))
+    return {k: np.array(v) for k, v in out.items()}
+
+
 if __name__ == "__main__":
+    for kind in ("velocity", "rpyt"):
+        for i, name in enumerate(["robobee", "tello"]):
+            fx = preprocess_fixture(kind, name, seed=300 + i)
+            np.savez_compressed(os.path.join(HERE, "pre_%s_%s.npz" % (kind, name)), **fx)
     np.savez_compressed(os.path.join(HERE, "wls_cases.npz"), **wls_fixture())
     np.savez_compressed(os.path.join(HERE, "quat_helpers.npz"), **quat_fixture())
     np.savez_compressed(os.path.join(HERE, "traj_3gates.npz"), **traj_fixture())

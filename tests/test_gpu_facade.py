@@ -135,3 +135,70 @@ def test_batched_facade_matches_single_env():
     assert (r8.cpu().numpy() == -1).all() and not d8.cpu().numpy().any()
     e1.close()
     e8.close()
+
+
+def test_velocity_aviary_closed_loop():
+    """examples/fly_INDI_velocity.py-style loop: VelocityAviary with a quad pair + a hexa, 1 s, against the oracle
+    (VelocityAviary._preprocessAction restated, then the AGGR_PHY_STEPS substeps)."""
+    _need_gpu()
+    from dronesim_b200.envs import Physics, VelocityAviary
+
+    models = ["robobee", "tello", "hexa_6DOF"]
+    init = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 1.2], [2.0, 0.5, 1.5]])
+    AGGR = 5
+    env = VelocityAviary(drone_model=models, num_drones=3, initial_xyzs=init, physics=Physics.PYB_DRAG, freq=240,
+                         aggregate_phy_steps=AGGR)
+    assert env.action_space["0"].shape == (4,) and abs(env.SPEED_LIMIT[0] - 30 / 3.6) < 1e-12
+    vts = [load_vehicle(m) for m in models]
+    orc = OracleSwarm(vts, 1, integrator="quat", composite=True, drag=True, aggregate_phy_steps=AGGR)
+    orc.reset(init)
+    env.reset()
+    rng = np.random.default_rng(11)
+    for i in range(48):
+        va = np.concatenate([rng.normal(0, 1, (3, 3)), rng.uniform(0.0, 0.08, (3, 1))], axis=1)
+        if i % 9 == 4:
+            va[1, 0:3] = 0.0  # zero direction -> zero target velocity (VelocityAviary.py:239-242)
+        obs, reward, done, info = env.step({str(j): va[j] for j in range(3)})
+        act = orc.velocity_preprocess(va.reshape(1, 3, 4))
+        orc.physics_step(act)
+        assert reward == -1 and done is False and info == {"answer": 42}
+    assert env.step_counter == orc.step_counter == 48 * AGGR
+    for j in range(3):
+        ref = orc.state_vector(0, j)
+        st = obs[str(j)]["state"]
+        assert np.abs(st[0:3] - ref[0:3]).max() <= 1e-4, (j, st[0:3], ref[0:3])
+        assert angle_between(st[3:7], ref[3:7]).max() <= 1e-4
+        np.testing.assert_allclose(st[16:], ref[16:], atol=1e-4)  # obs tail = the applied (preprocessed) PWM command
+    env.close()
+
+
+def test_rpyt_aviary_closed_loop():
+    """RPYTAviary: body-rate + thrust actions through INDIControl._INDIRateControl, two quads, 0.5 s."""
+    _need_gpu()
+    from dronesim_b200.envs import Physics, RPYTAviary
+
+    models = ["robobee", "tello"]
+    init = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 1.2]])
+    AGGR = 2
+    env = RPYTAviary(drone_model=models, num_drones=2, initial_xyzs=init, physics=Physics.PYB, freq=240, aggregate_phy_steps=AGGR)
+    vts = [load_vehicle(m) for m in models]
+    orc = OracleSwarm(vts, 1, integrator="quat", composite=True, aggregate_phy_steps=AGGR)
+    orc.reset(init)
+    env.reset()
+    rng = np.random.default_rng(12)
+    thrust = np.array([0.2, 0.2])
+    for i in range(60):
+        thrust = np.clip(thrust + rng.normal(0, 0.01, 2), 0.0, 1.0)
+        rt = np.concatenate([rng.normal(0, 0.2, (2, 3)), thrust[:, None]], axis=1)
+        obs, _, _, _ = env.step({str(j): rt[j] for j in range(2)})
+        orc.physics_step(orc.rate_preprocess(rt.reshape(1, 2, 4)))
+    for j in range(2):
+        ref = orc.state_vector(0, j)
+        st = obs[str(j)]["state"]
+        assert np.abs(st[0:3] - ref[0:3]).max() <= 1e-4
+        assert angle_between(st[3:7], ref[3:7]).max() <= 1e-4
+        np.testing.assert_allclose(st[16:20], ref[16:20], atol=1e-4)
+    with pytest.raises(Exception):  # the 6-DOF law has no rate / thrust entry
+        e2 = RPYTAviary(drone_model=["hexa_6DOF"], num_drones=1, initial_xyzs=np.array([[0, 0, 1.0]]))
+        e2.step({"0": np.array([0, 0, 0, 0.3])})
+    env.close()

@@ -444,3 +444,34 @@ def test_symmetric_downwash_pairs_match_ordered_pairs():
     np.testing.assert_allclose(outs[0][0], outs[1][0], atol=2e-5)
     np.testing.assert_allclose(outs[0][1], outs[1][1], atol=2e-4)
     np.testing.assert_allclose(outs[0][2], outs[1][2], atol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------
+# velocity-command and rate/thrust-command target modes against fixtures produced by calling the
+# reference's VelocityAviary._preprocessAction / RPYTAviary._preprocessAction
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["velocity", "rpyt"])
+@pytest.mark.parametrize("name", ["robobee", "tello"])
+def test_preprocess_action_modes_vs_reference_fixture(kind, name):
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    g = np.load(os.path.join(GOLD, "pre_%s_%s.npz" % (kind, name)))
+    S, T = g["states"].shape[:2]
+    for sq in range(S):  # AGGR_PHY_STEPS (hence control_timestep) differs per recorded sequence
+        K = int(g["aggr"][sq, 0])
+        core = SwarmCore([name], 1, aggregate_phy_steps=K)
+        core.reset(np.zeros((1, 3)))
+        for t in range(T):
+            st = np.zeros((1, 22), dtype=np.float32)
+            st[0, :20] = g["states"][sq, t]
+            a = g["action"][sq, t].reshape(1, 4)
+            tgt = core.targets_velocity(a) if kind == "velocity" else core.targets_rate_thrust(a)
+            cmd, _, _ = core.control_from_state(torch.tensor(st, device="cuda"), tgt, K / 240.0)
+            err = np.abs(cmd.cpu().numpy()[0, :4] - g["cmd"][sq, t]).max()
+            assert err <= 2e-5, "%s/%s cmd error %.3e at step %d of sequence %d (PWM units)" % (kind, name, err, t, sq)
+            v = core.views()
+            np.testing.assert_allclose(v["last_rates"].cpu().numpy()[0], g["last_rates"][sq, t], atol=2e-5)
+            ref_lt = float(g["last_thrust"][sq, t])
+            np.testing.assert_allclose(v["last_thrust"].cpu().numpy()[0], ref_lt, atol=2e-5 * max(1.0, abs(ref_lt)))
+        core.close()

@@ -112,3 +112,36 @@ def test_oracle_vs_live_reference_classes(name):
         np.testing.assert_allclose(np.array(a[0], float), b[0], atol=1e-10)
         np.testing.assert_allclose(np.array(a[1], float), b[1], atol=1e-13)
         assert abs(float(a[2]) - b[2]) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# VelocityAviary / RPYTAviary ``_preprocessAction``: the oracle's restatement against
+# fixtures produced by calling the reference's own methods (tests/golden/make_golden.py::preprocess_fixture)
+# ------------------------------------------------------------------------------------------
+def _set_oracle_state(orc, st):
+    from oracle import pyb_math as p
+
+    orc.pos[0, 0], orc.quat[0, 0], orc.rpy[0, 0], orc.vel[0, 0] = st[0:3], st[3:7], st[7:10], st[10:13]
+    orc.rates[0, 0] = p.rotmat(st[3:7]).T.dot(st[13:16])  # the oracle keeps body rates
+
+
+@pytest.mark.parametrize("kind", ["velocity", "rpyt"])
+@pytest.mark.parametrize("name", ["robobee", "tello"])
+def test_preprocess_action_vs_reference_fixture(kind, name):
+    from oracle.sim import OracleSwarm
+
+    g = np.load(os.path.join(GOLD, "pre_%s_%s.npz" % (kind, name)))
+    S, T = g["states"].shape[:2]
+    for sq in range(S):
+        orc = OracleSwarm([load_vehicle(name)], 1, aggregate_phy_steps=int(g["aggr"][sq, 0]))
+        orc.reset(np.zeros((1, 3)))
+        for t in range(T):
+            _set_oracle_state(orc, g["states"][sq, t])
+            fn = orc.velocity_preprocess if kind == "velocity" else orc.rate_preprocess
+            act = fn(g["action"][sq, t].reshape(1, 1, 4))
+            np.testing.assert_allclose(act[0, 0, :4], g["cmd"][sq, t], rtol=0, atol=1e-12)
+            c = orc.ctrl[0][0]
+            np.testing.assert_allclose(c.last_rates, g["last_rates"][sq, t], atol=1e-12)
+            np.testing.assert_allclose(c.last_thrust, g["last_thrust"][sq, t], atol=1e-12)
+            if kind == "velocity":
+                np.testing.assert_allclose(c.last_vel, g["last_vel"][sq, t], atol=1e-12)

@@ -18,6 +18,7 @@ struct ds_handle {
   int n_types = 0;
   bool types_set = false, is_reset = false;
   bool nu6 = false;
+  int rc_kind = 0;                    // 0: no type has a centre-of-mass offset, 1: some general offset, 2: offsets along body z only
   bool any_6dof = false;              // some type flies the 6-DOF law (no rate / thrust entry: INDIControl_6DOF has none)
   bool dw_uniform = true;             // every type shares DW_COEFF_2 / DW_COEFF_3 (symmetric downwash pairs allowed)
   bool first_action_pending = false;  // s_a holds the caller's initial action (fly_INDI.py:214)
@@ -225,7 +226,9 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     }
     d.rpm0_sum = (float)rpm0;
     if (p.n_u > 4) h->nu6 = true;
-    if (t == 0) h->any_6dof = false;
+    if (t == 0) { h->any_6dof = false; h->rc_kind = 0; }
+    if (d.has_rc == 1) h->rc_kind = 1;
+    else if (d.has_rc == 2 && h->rc_kind == 0) h->rc_kind = 2;
     if (p.law == DS_LAW_6DOF) h->any_6dof = true;
     if (t == 0) h->dw_uniform = true;
     else if (d.dw_k2 != dev[0].dw_k2 || d.dw_k3 != dev[0].dw_k3) h->dw_uniform = false;
@@ -323,6 +326,7 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.types = h->d_types; a.wls = h->d_wls; a.slot_type = h->d_slot_type; a.stats = h->d_stats;
   a.n = h->n; a.D = h->cfg.drones_per_env; a.tile_v = h->tile_v; a.n_tiles = h->n_tiles;
   a.K = h->cfg.substeps; a.n_types = h->n_types;
+  a.rc_kind = h->rc_kind;
   a.flags = h->cfg.flags & 0xFu;
   a.dt = 1.0f / h->cfg.sim_freq;
   a.gravity = h->cfg.gravity;

@@ -84,6 +84,7 @@ struct DsArgs {
   int n_types;
   uint32_t flags;
   int order;
+  int rc_kind;      // centre-of-mass offsets of the swarm's types: 0 none, 1 some general offset, 2 all along body z
   int use_act;      // physics reads the action from s_a0/s_a1 instead of the controller cmd
   int store_act;    // physics stores the clipped action to s_a0/s_a1
   float dt;         // TIMESTEP

@@ -153,8 +153,8 @@ __device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict_
 // act[] must already be clipped.  prev_rpm_sum: in = sum of rpm of the previously applied action
 // (BaseAviary.py:532), out = sum of rpm of this action.
 // FX >= 0: ground effect (bit 0) / drag (bit 1) resolved at compile time; FX < 0: run-time a.flags.
-// Centre-of-mass offset rc (QUAT integrator only; tp.has_rc: 0 none, 1 general, 2 along body z only - the shipped
-// hexa): the state is integrated at the centre of mass, the add-ons that the reference applies at the base-frame
+// Centre-of-mass offset rc (QUAT integrator only; DsTypeDev::has_rc: 0 none, 1 general, 2 along body z only): the
+// state is integrated at the centre of mass, the add-ons that the reference applies at the base-frame
 // origin (drag, downwash: R7 of oracle/dynamics.py) see p_base = c - R rc, v_base = u - R (w x rc) and add the
 // torque (-rc) x f.
 template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX>
@@ -164,7 +164,10 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   const float dt = a.dt;
   const bool gnd = (FX >= 0) ? ((FX & 1) != 0) : ((a.flags & 1u) != 0);
   const bool drag = (FX >= 0) ? ((FX & 2) != 0) : ((a.flags & 2u) != 0);
-  const int rc_kind = (INTEG == 0) ? tp.has_rc : 0;  // per type (quads of the shipped URDFs have none)
+  // a.rc_kind is the same for every lane (1 if some type of the swarm has a general offset, 2 if all offsets are along
+  // z, 0 if none): types without an offset run the same arithmetic with rc = 0, which is exact (x + 0 = x), so a warp
+  // that mixes airframes does not diverge here
+  const int rc_kind = (INTEG == 0) ? a.rc_kind : 0;
   const bool has_rc = rc_kind != 0;
   const bool rc_gen = rc_kind == 1;
 

@@ -249,7 +249,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or min(args.steps, 48)
-        chunk = 8
+        chunk = 16  # control steps per ds_rollout_host call (1 GiB of pinned targets at 4 Mi vehicles)
         e2e_steps = max(chunk, (e2e_steps // chunk) * chunk)
         # (1) pipelined rollout: targets of `chunk` control steps per call, H2D / D2H overlapped with the compute
         h_roll = torch.from_numpy(tgt32).unsqueeze(0).repeat(chunk, 1, 1).contiguous().pin_memory()

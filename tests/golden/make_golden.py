@@ -14,6 +14,9 @@ three PyBullet math functions and an empty gym):
 * dronesim/utils/trajGen.py             -> traj_3gates.npz (the table of examples/fly_INDI_TrajectoryTrack.py:127-160)
 * dronesim/envs/VelocityAviary.py       -> pre_velocity_<vehicle>.npz (``_preprocessAction`` :221-264, called unbound)
 * dronesim/envs/RPYTAviary.py           -> pre_rpyt_<vehicle>.npz     (``_preprocessAction`` :180-193, called unbound)
+* dronesim/envs/BaseAviary.py           -> dyn_<vehicle>.npz (``_dynamics`` :1767-1828, ``_drag`` :1705-1732, ``_downwash``
+                                           :1736-1763, ``_groundEffect`` :1648-1699 called unbound on a stand-in ``self``
+                                           with a recording stand-in for the module's ``p``)
 
 The fixtures are small .npz files; they are what travels to the GPU box (the reference does not).
 """
@@ -197,7 +200,106 @@ def preprocess_fixture(kind, name, seed, T=30, n_seq=4):
     return {k: np.array(v) for k, v in out.items()}
 
 
+class _RecordingBullet:
+    """Stand-in for the ``pybullet`` module object the reference's BaseAviary methods call: the three math functions
+    plus recorders for the calls that hand forces / states to the physics engine."""
+
+    LINK_FRAME = 1
+
+    def __init__(self):
+        self.forces, self.reset_pose, self.reset_vel, self.link_pos = [], None, None, None
+        self.getMatrixFromQuaternion = pyb_math.getMatrixFromQuaternion
+        self.getQuaternionFromEuler = pyb_math.getQuaternionFromEuler
+        self.getEulerFromQuaternion = pyb_math.getEulerFromQuaternion
+
+    def applyExternalForce(self, body, link, forceObj, posObj, flags, physicsClientId):
+        self.forces.append((int(link), np.array(forceObj, float), int(flags)))
+
+    def resetBasePositionAndOrientation(self, body, pos, quat, physicsClientId):
+        self.reset_pose = (np.array(pos, float), np.array(quat, float))
+
+    def resetBaseVelocity(self, body, vel, ang, physicsClientId):
+        self.reset_vel = (np.array(vel, float), np.array(ang, float))
+
+    def getLinkStates(self, body, linkIndices, computeLinkVelocity, computeForwardKinematics, physicsClientId):
+        # the reference reads link_states[i, 0][2] only (BaseAviary.py:1672-1679): entry 0 = link world position
+        return [[list(self.link_pos[i])] + [[0.0, 0.0, 0.0]] * 7 for i in linkIndices]
+
+
+def dynamics_fixture(name, seed, n_cases=48):
+    """``BaseAviary._dynamics / _drag / _downwash / _groundEffect`` (BaseAviary.py:1767-1828, 1705-1732, 1736-1763,
+    1648-1699) are dead code INSIDE the reference (their ``self.KF, self.M, ...`` are never assigned, ``x_torque`` is
+    unbound for a list ``DRONE_MODEL``) but their bodies execute unchanged when called UNBOUND on a stand-in ``self``
+    that supplies those attributes, with the module's ``p`` replaced by a recorder.  The stand-in describes a quad
+    whose arm matches its URDF rotor sites (``L / sqrt(2)`` = the rotor x offset, CF2X layout), so the fixture pins
+    the formulas; the per-drone / rotor-geometry generalisations (repairs R1-R7 of oracle/dynamics.py) remain restated."""
+    import types
+
+    import dronesim.envs.BaseAviary as BA
+    from dronesim_b200.vehicles import load_vehicle
+
+    vt = load_vehicle(name)
+    rng = np.random.default_rng(seed)
+    rec = _RecordingBullet()
+    BA.p = rec  # the module-level name the methods resolve at call time
+    arm = abs(float(vt.rotor_pos[0][0])) * np.sqrt(2.0)
+    out = {k: [] for k in ("pos", "rpy", "quat", "vel", "rates", "cmd", "rpm", "dyn_pos", "dyn_quat", "dyn_vel", "dyn_rates",
+                           "drag_force", "others", "dw_force", "gnd_rpy", "gnd_forces", "gnd_heights")}
+    for c in range(n_cases):
+        pos = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.02, 2.0)])
+        rpy = rng.uniform(-0.6, 0.6, 3)
+        quat = np.array(pyb_math.getQuaternionFromEuler(rpy))
+        vel = rng.normal(0, 1.0, 3)
+        rates = rng.normal(0, 1.0, 3)
+        cmd = rng.uniform(0.2, 0.9, 4)
+        rpm = np.array(vt.PWM2RPM_SCALE) * cmd + np.array(vt.PWM2RPM_CONST)  # BaseAviary.py:1487-1490
+        others = pos + np.concatenate([rng.uniform(-0.6, 0.6, (3, 2)), rng.uniform(-0.8, 1.5, (3, 1))], axis=1)
+        if c % 8 == 5:
+            others[0, 0:2] = pos[0:2] + [11.0, 0.0]  # beyond the 10 m gate (:1752)
+        self = types.SimpleNamespace(
+            pos=np.vstack([pos, others]), quat=np.tile(quat, (4, 1)), rpy=np.tile(rpy, (4, 1)),
+            vel=np.tile(vel, (4, 1)), rpy_rates=np.tile(rates, (4, 1)), NUM_DRONES=4, DRONE_IDS=[1, 2, 3, 4], CLIENT=0,
+            KF=vt.KF, KM=vt.KM, M=vt.M, GRAVITY=9.8 * vt.M, L=arm, J=np.array(vt.J), J_INV=np.array(vt.J_INV),
+            TIMESTEP=1.0 / 240, DRONE_MODEL=BA.DroneModel.CF2X, DRAG_COEFF=np.array(vt.DRAG_COEFF),
+            DW_COEFF_1=vt.DW_COEFF_1, DW_COEFF_2=vt.DW_COEFF_2, DW_COEFF_3=vt.DW_COEFF_3, PROP_RADIUS=vt.PROP_RADIUS,
+            GND_EFF_COEFF=vt.GND_EFF_COEFF, GND_EFF_H_CLIP=vt.GND_EFF_H_CLIP)
+        # _dynamics
+        BA.BaseAviary._dynamics(self, rpm, 0)
+        dyn_pos, dyn_quat = rec.reset_pose
+        dyn_vel = rec.reset_vel[0]
+        dyn_rates = self.rpy_rates[0].copy()
+        # _drag
+        rec.forces = []
+        BA.BaseAviary._drag(self, rpm, 0)
+        assert len(rec.forces) == 1 and rec.forces[0][0] == 4 and rec.forces[0][2] == rec.LINK_FRAME
+        drag_force = rec.forces[0][1]
+        # _downwash
+        rec.forces = []
+        BA.BaseAviary._downwash(self, 0)
+        dw_force = np.sum([f for _, f, _ in rec.forces], axis=0) if rec.forces else np.zeros(3)
+        # _groundEffect: rotor link world positions from the URDF rotor sites (what getLinkStates reports)
+        R = pyb_math.rotmat(quat)
+        rec.link_pos = [pos + R.dot(np.array(vt.rotor_pos[i])) for i in range(4)] + [pos]
+        grpy = rpy.copy()
+        if c % 8 == 6:
+            grpy[0] = 1.7  # beyond the pi/2 gate (:1687-1690)
+        self.rpy = np.tile(grpy, (4, 1))
+        rec.forces = []
+        BA.BaseAviary._groundEffect(self, rpm, 0)
+        gnd = np.zeros((4, 3))
+        for link, f, _ in rec.forces:
+            gnd[link] = f
+        for k, v in (("pos", pos), ("rpy", rpy), ("quat", quat), ("vel", vel), ("rates", rates), ("cmd", cmd), ("rpm", rpm),
+                     ("dyn_pos", dyn_pos), ("dyn_quat", dyn_quat), ("dyn_vel", dyn_vel), ("dyn_rates", dyn_rates),
+                     ("drag_force", drag_force), ("others", others), ("dw_force", dw_force), ("gnd_rpy", grpy),
+                     ("gnd_forces", gnd), ("gnd_heights", np.array([lp[2] for lp in rec.link_pos[:4]]))):
+            out[k].append(np.array(v, float))
+    return {k: np.array(v) for k, v in out.items()}
+
+
 if __name__ == "__main__":
+    for i, name in enumerate(["robobee", "tello"]):
+        np.savez_compressed(os.path.join(HERE, "dyn_%s.npz" % name), **dynamics_fixture(name, seed=400 + i))
     for kind in ("velocity", "rpyt"):
         for i, name in enumerate(["robobee", "tello"]):
             fx = preprocess_fixture(kind, name, seed=300 + i)

@@ -475,3 +475,30 @@ def test_preprocess_action_modes_vs_reference_fixture(kind, name):
             ref_lt = float(g["last_thrust"][sq, t])
             np.testing.assert_allclose(v["last_thrust"].cpu().numpy()[0], ref_lt, atol=2e-5 * max(1.0, abs(ref_lt)))
         core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# one `_dynamics` substep against fixtures produced by EXECUTING the reference's own BaseAviary._dynamics body
+# (tests/golden/make_golden.py::dynamics_fixture); the add-on force formulas are pinned the same way on the CPU side
+# (tests/test_oracle_dynamics.py) and reach the GPU through test_physics_step_external_action
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["robobee", "tello"])
+def test_dynamics_substep_vs_reference_fixture(name):
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    g = np.load(os.path.join(GOLD, "dyn_%s.npz" % name))
+    n = g["pos"].shape[0]
+    core = SwarmCore([name], n, integrator="rpy", composite=False, aggregate_phy_steps=1)
+    core.reset(g["pos"], rpy0=g["rpy"], vel0=g["vel"])
+    core.views()["omega_body"][:] = torch.tensor(g["rates"], dtype=torch.float32, device="cuda")  # rpy_rates (:1787)
+    act = np.zeros((n, 6), dtype=np.float32)
+    act[:, :4] = g["cmd"]
+    core.physics_step(torch.tensor(act, device="cuda"))
+    torch.cuda.synchronize()
+    st = core_state(core)
+    np.testing.assert_allclose(st["pos"], g["dyn_pos"], atol=2e-6)
+    np.testing.assert_allclose(st["vel"], g["dyn_vel"], atol=1e-5)
+    np.testing.assert_allclose(st["omega_body"], g["dyn_rates"], rtol=2e-5, atol=2e-4)
+    assert angle_between(st["quat"], g["dyn_quat"]).max() <= 2e-6
+    core.close()

@@ -22,8 +22,11 @@ the reference checkout, enac-drones/dronesim):
 
 Parity pinning: the control half is pinned against the reference's own code executed behind
 ``ref_shims`` (fixtures in ``tests/golden/``, generator ``tests/golden/make_golden.py``) and
-against the one known-answer test the reference ships (``wls_alloc.py:381-408``).  The dynamics
-half restates formulas that cannot run in the reference (dead code + PyBullet absent):
-**parity unpinned** for the dynamics half and for the Bullet math trio (self-consistency and
-scipy cross-checks only).
+against the one known-answer test the reference ships (``wls_alloc.py:381-408``); so are the
+``VelocityAviary`` / ``RPYTAviary`` ``_preprocessAction`` restatements and the ``Logger`` data model.
+The dynamics half restates formulas the reference cannot step (dead code + PyBullet absent), but
+whose bodies run unbound on a stand-in ``self``: pinned that way for the 4-rotor airframes
+(``dyn_*.npz``); the rotor-geometry generalisation for the hexa and the quaternion integrator are
+restated only - **parity unpinned** for those two and for the Bullet math trio
+(self-consistency and scipy cross-checks only).
 """

@@ -1,10 +1,15 @@
 """FP64 restatement of the reference's explicit dynamics and aerodynamic add-ons.
 
-TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  **Parity unpinned**: the functions restated
-here are dead code in the reference fork (they read ``self.KF, self.M, self.J ...`` whose
-assignments are commented out, BaseAviary.py:200-216,226-235) and the live path needs PyBullet,
-so they cannot be executed to produce fixtures.  The formulas are the spec; each deviation
-("repair") is listed below with the reference line it replaces.
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  The functions restated here are dead code INSIDE
+the reference fork (they read ``self.KF, self.M, self.J ...`` whose assignments are commented out,
+BaseAviary.py:200-216,226-235, and the live path needs PyBullet), so the reference cannot step
+them.  Their bodies do execute when called unbound on a stand-in ``self`` with a recording stand-in
+for the module's ``p``: ``tests/golden/dyn_{robobee,tello}.npz`` hold the outputs of the reference's own
+``_dynamics / _drag / _downwash / _groundEffect`` run that way (tests/golden/make_golden.py::
+dynamics_fixture) and ``tests/test_oracle_dynamics.py`` pins this module to them to 1e-12.
+**Pinned for the 4-rotor airframes; the generalisations that let the same formulas fly a
+heterogeneous list and the tilted-rotor hexa (repairs R1-R7 below) and the ``"quat"`` integrator (R8,
+beyond the reference) are restated, not pinned.**  Each repair is listed with the reference line it replaces.
 
 Restated (dronesim/envs/BaseAviary.py):
 * motor map            :1487-1490, :1398-1401   rpm = PWM2RPM_SCALE * cmd + PWM2RPM_CONST

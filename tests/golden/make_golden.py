@@ -17,6 +17,8 @@ three PyBullet math functions and an empty gym):
 * dronesim/envs/BaseAviary.py           -> dyn_<vehicle>.npz (``_dynamics`` :1767-1828, ``_drag`` :1705-1732, ``_downwash``
                                            :1736-1763, ``_groundEffect`` :1648-1699 called unbound on a stand-in ``self``
                                            with a recording stand-in for the module's ``p``)
+                                        -> rotor_<vehicle>.npz (the LIVE ``_quad_copter_physics`` :1477-1543 /
+                                           ``_morphing_hexa_physics`` :1389-1457, noise source zeroed)
 
 The fixtures are small .npz files; they are what travels to the GPU box (the reference does not).
 """
@@ -207,13 +209,16 @@ class _RecordingBullet:
     LINK_FRAME = 1
 
     def __init__(self):
-        self.forces, self.reset_pose, self.reset_vel, self.link_pos = [], None, None, None
+        self.forces, self.torques, self.reset_pose, self.reset_vel, self.link_pos = [], [], None, None, None
         self.getMatrixFromQuaternion = pyb_math.getMatrixFromQuaternion
         self.getQuaternionFromEuler = pyb_math.getQuaternionFromEuler
         self.getEulerFromQuaternion = pyb_math.getEulerFromQuaternion
 
     def applyExternalForce(self, body, link, forceObj, posObj, flags, physicsClientId):
         self.forces.append((int(link), np.array(forceObj, float), int(flags)))
+
+    def applyExternalTorque(self, body, link, torqueObj, flags, physicsClientId):
+        self.torques.append((int(link), np.array(torqueObj, float), int(flags)))
 
     def resetBasePositionAndOrientation(self, body, pos, quat, physicsClientId):
         self.reset_pose = (np.array(pos, float), np.array(quat, float))
@@ -297,7 +302,47 @@ def dynamics_fixture(name, seed, n_cases=48):
     return {k: np.array(v) for k, v in out.items()}
 
 
+def rotor_fixture(name, seed, n_cases=24):
+    """The LIVE rotor force models ``_quad_copter_physics`` (BaseAviary.py:1477-1543) / ``_morphing_hexa_physics``
+    (:1389-1457) called unbound: PWM -> RPM map, KF rpm^2 / KM rpm^2, spin signs, the link every force / torque is
+    applied to.  The unseeded ``np.random.normal`` noise source (:1429-1432, 1518-1525) is replaced by zeros for the
+    duration of the call - the noise-off mode all parity runs use."""
+    import types
+
+    import dronesim.envs.BaseAviary as BA
+    from dronesim_b200.vehicles import load_vehicle
+
+    vt = load_vehicle(name)
+    n_u = vt.INDI_ACTUATOR_NR
+    rng = np.random.default_rng(seed)
+    rec = _RecordingBullet()
+    BA.p = rec
+    drone = types.SimpleNamespace(PWM2RPM_SCALE=np.array(vt.PWM2RPM_SCALE), PWM2RPM_CONST=np.array(vt.PWM2RPM_CONST),
+                                  KF=vt.KF, KM=vt.KM, INDI_ACTUATOR_NR=n_u, TYPE=vt.TYPE)
+    self = types.SimpleNamespace(drones=[drone], DRONE_IDS=[1], CLIENT=0, quat=np.array([[0, 0, 0, 1.0]]), vel=np.zeros((1, 3)))
+    fn = BA.BaseAviary._morphing_hexa_physics if n_u == 6 else BA.BaseAviary._quad_copter_physics
+    out = dict(cmd=[], force_link=[], force=[], torque_link=[], torque=[])
+    real_normal = np.random.normal
+    np.random.normal = lambda loc, scale, size=None: np.zeros(size)
+    try:
+        for _ in range(n_cases):
+            cmd = rng.uniform(0.0, 1.0, n_u)
+            rec.forces, rec.torques = [], []
+            fn(self, cmd, 0)
+            out["cmd"].append(cmd)
+            out["force_link"].append([l for l, _, _ in rec.forces])
+            out["force"].append([f for _, f, _ in rec.forces])
+            out["torque_link"].append([l for l, _, _ in rec.torques])
+            out["torque"].append([t for _, t, _ in rec.torques])
+            assert all(fl == rec.LINK_FRAME for _, _, fl in rec.forces + rec.torques)
+    finally:
+        np.random.normal = real_normal
+    return {k: np.array(v, float) for k, v in out.items()}
+
+
 if __name__ == "__main__":
+    for i, name in enumerate(["robobee", "tello", "hexa_6DOF", "hexa_6DOF_simple"]):
+        np.savez_compressed(os.path.join(HERE, "rotor_%s.npz" % name), **rotor_fixture(name, seed=500 + i))
     for i, name in enumerate(["robobee", "tello"]):
         np.savez_compressed(os.path.join(HERE, "dyn_%s.npz" % name), **dynamics_fixture(name, seed=400 + i))
     for kind in ("velocity", "rpyt"):

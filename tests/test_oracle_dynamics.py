@@ -60,3 +60,38 @@ def test_add_on_forces_vs_reference_methods(name):
         h = [g["pos"][c][2] + R[2, :].dot(pp.rotor_pos[i]) for i in range(4)]
         np.testing.assert_allclose(h, g["gnd_heights"][c], atol=1e-14)
     assert gated_gnd >= 1  # the |roll| >= pi/2 gate is exercised
+
+
+@pytest.mark.parametrize("name", ["robobee", "tello", "hexa_6DOF", "hexa_6DOF_simple"])
+def test_rotor_forces_vs_live_reference_functions(name):
+    """``_quad_copter_physics`` (BaseAviary.py:1477-1543) / ``_morphing_hexa_physics`` (:1389-1457) are LIVE reference code;
+    the fixture records what they hand to PyBullet (noise source zeroed).  Pinned here: PWM -> RPM map, KF rpm^2,
+    KM rpm^2 with the spin signs, and the link each force is applied to (what the loader takes rotor sites from)."""
+    g = np.load(os.path.join(GOLD, "rotor_%s.npz" % name))
+    vt = load_vehicle(name)
+    pp = od.PhysParams(vt, composite=True)
+    n_u = pp.n_u
+    hexa = n_u == 6
+    for c in range(g["cmd"].shape[0]):
+        rpm = od.rpm_of_cmd(pp, g["cmd"][c])
+        T, Q = pp.kf * rpm**2, pp.km * rpm**2
+        # forces: [0, 0, T_j] in the LINK frame of link 2j+1 (hexa, :1442) / link j (quad, :1528)
+        np.testing.assert_array_equal(g["force_link"][c], [2 * j + 1 for j in range(n_u)] if hexa else list(range(n_u)))
+        np.testing.assert_allclose(g["force"][c][:, 2], T, rtol=1e-12)
+        assert not g["force"][c][:, :2].any()
+        if hexa:  # torque [0, 0, -/+ Q_j] on the same link, rotors 0, 2, 4 flipped (:1439-1440)
+            np.testing.assert_array_equal(g["torque_link"][c], g["force_link"][c])
+            np.testing.assert_allclose(g["torque"][c][:, 2], pp.spin * Q, rtol=1e-12)
+        else:  # one base-link torque -t0 + t1 - t2 + t3 about base z (:1527, 1537-1543)
+            np.testing.assert_array_equal(g["torque_link"][c], [-1])
+            np.testing.assert_allclose(g["torque"][c][0, 2], float(np.sum(pp.spin * Q)), rtol=1e-10, atol=1e-16)
+            np.testing.assert_allclose(pp.torque_axis, np.tile([0.0, 0.0, 1.0], (n_u, 1)))
+        # the body wrench the oracle (and the CUDA core) integrates is exactly these link-frame vectors moved to the
+        # centre of mass with the loader's link geometry
+        F, tau, _ = od.body_wrench(pp, g["cmd"][c], 0.0, np.zeros(3), np.array([0, 0, 0, 1.0]), np.zeros(3), np.zeros(3), [],
+                                   False, False, False)
+        Fx = sum(g["force"][c][j, 2] * pp.rotor_axis[j] for j in range(n_u))
+        tq = sum(np.cross(pp.rotor_pos[j] - pp.r_com, g["force"][c][j, 2] * pp.rotor_axis[j]) for j in range(n_u))
+        tq = tq + (sum(g["torque"][c][j, 2] * pp.torque_axis[j] for j in range(n_u)) if hexa else g["torque"][c][0])
+        np.testing.assert_allclose(F, Fx, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(tau, tq, rtol=1e-10, atol=1e-14)

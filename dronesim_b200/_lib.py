@@ -39,6 +39,7 @@ class ds_config(C.Structure):
         ("neighbourhood_radius", C.c_float), ("done_goal_enable", C.c_int32), ("goal", C.c_float * 3),
         ("goal_radius", C.c_float), ("done_floor_enable", C.c_int32), ("z_min", C.c_float),
         ("max_steps", C.c_int32), ("env_offset", C.c_int32),
+        ("motor_tau", C.c_float), ("acc_filter_hz", C.c_float), ("reward_mode", C.c_int32),
     ]
 
 
@@ -72,6 +73,7 @@ class ds_state_views(C.Structure):
         ("pos_thrust", C.c_void_p), ("quat", C.c_void_p), ("vel_rpm", C.c_void_p), ("omega_wp", C.c_void_p),
         ("lastvel_done", C.c_void_p), ("lastrates_err", C.c_void_p), ("cmd0123", C.c_void_p), ("cmd45", C.c_void_p),
         ("slot_type", C.c_void_p), ("step_counter", C.c_int64),
+        ("rpm0123", C.c_void_p), ("rpm45", C.c_void_p), ("ang_acc_filt", C.c_void_p),
     ]
 
 

@@ -83,7 +83,8 @@ class SwarmCore:
                  ground: bool = False, drag: bool = False, downwash: bool = False, stats: bool = False,
                  freq: float = 240.0, aggregate_phy_steps: int = 1, neighbourhood_radius: float = math.inf,
                  gravity: float = 9.8, goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0,
-                 device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None, dw_ordered_pairs: bool = False):
+                 device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None, dw_ordered_pairs: bool = False,
+                 motor_tau: float = 0.0, acc_filter_hz: float = 0.0, reward_mode: int = 0):
         lib = L.lib()
         self.vehicle_types: List[VehicleType] = [m if isinstance(m, VehicleType) else load_vehicle(m, assets_dir)
                                                  for m in slot_models]
@@ -112,6 +113,8 @@ class SwarmCore:
         if z_min is not None:
             cfg.done_floor_enable, cfg.z_min = 1, float(z_min)
         cfg.max_steps, cfg.env_offset = int(max_steps), int(env_offset)
+        # extensions beyond the reference (north_star): first-order motor lag, low-passed angular acceleration, tracking reward
+        cfg.motor_tau, cfg.acc_filter_hz, cfg.reward_mode = float(motor_tau), float(acc_filter_hz), int(reward_mode)
         self._h = C.c_void_p()
         L.check(lib.ds_create(C.byref(cfg), C.byref(self._h)))
         # distinct types, in order of first appearance
@@ -301,7 +304,11 @@ class SwarmCore:
 
         pos_t, quat, vel_r, om_w = f4(v.pos_thrust), f4(v.quat), f4(v.vel_rpm), f4(v.omega_wp)
         lv_d, lr_e, c0, c1 = f4(v.lastvel_done), f4(v.lastrates_err), f4(v.cmd0123), f4(v.cmd45, 2)
+        ext = {}
+        if v.rpm0123:
+            ext = {"rpm": torch.cat([f4(v.rpm0123), f4(v.rpm45, 2)], dim=1), "ang_acc_filt": f4(v.ang_acc_filt)[:, :3]}
         return {
+            **ext,
             "pos": pos_t[:, :3], "last_thrust": pos_t[:, 3], "quat": quat, "vel": vel_r[:, :3], "rpm_sum": vel_r[:, 3],
             "omega_body": om_w[:, :3], "wp_counter": om_w.view(torch.int32)[:, 3], "last_vel": lv_d[:, :3],
             "done_bits": lv_d.view(torch.int32)[:, 3], "last_rates": lr_e[:, :3], "pos_err": lr_e[:, 3],

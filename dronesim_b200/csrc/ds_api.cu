@@ -31,6 +31,9 @@ struct ds_handle {
   float4 *s_pos = nullptr, *s_quat = nullptr, *s_vel = nullptr, *s_om = nullptr, *s_lv = nullptr, *s_lr = nullptr;
   float4 *s_c0 = nullptr, *s_a0 = nullptr;
   float2 *s_c1 = nullptr, *s_a1 = nullptr;
+  float4 *s_r0 = nullptr, *s_af = nullptr;  // extension state: rotor speeds, filtered angular acceleration
+  float2* s_r1 = nullptr;
+  bool ext = false;
   DsTypeDev* d_types = nullptr;
   DsWlsDev* d_wls = nullptr;
   uint8_t* d_slot_type = nullptr;
@@ -82,7 +85,7 @@ static void free_all(ds_handle* h) {
   void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
                   h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
-                  h->d_roll_done[1], h->d_log_ids, h->d_log_states};
+                  h->d_roll_done[1], h->d_log_ids, h->d_log_states, h->s_r0, h->s_r1, h->s_af};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; ++b) {
@@ -101,6 +104,9 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   if (cfg->drones_per_env > DS_MAX_DRONES_PER_ENV) return DS_ERR_UNSUPPORTED;
   if (cfg->integrator != DS_INTEG_QUAT && cfg->integrator != DS_INTEG_RPY) return DS_ERR_INVALID;
   if ((int64_t)cfg->n_envs * cfg->drones_per_env > (int64_t)1 << 30) return DS_ERR_UNSUPPORTED;
+  if (cfg->motor_tau < 0.f || cfg->acc_filter_hz < 0.f || cfg->reward_mode < 0 || cfg->reward_mode > 1) return DS_ERR_INVALID;
+  const bool want_ext = cfg->motor_tau > 0.f || cfg->acc_filter_hz > 0.f;
+  if (want_ext && cfg->integrator == DS_INTEG_RPY) return DS_ERR_UNSUPPORTED;
   ds_handle* h = new (std::nothrow) ds_handle();
   if (!h) return DS_ERR_INVALID;
   h->cfg = *cfg;
@@ -126,6 +132,8 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   alloc((void**)&h->s_om, np * 16);  alloc((void**)&h->s_lv, np * 16);   alloc((void**)&h->s_lr, np * 16);
   alloc((void**)&h->s_c0, np * 16);  alloc((void**)&h->s_a0, np * 16);
   alloc((void**)&h->s_c1, np * 8);   alloc((void**)&h->s_a1, np * 8);
+  h->ext = want_ext;
+  if (want_ext) { alloc((void**)&h->s_r0, np * 16); alloc((void**)&h->s_r1, np * 8); alloc((void**)&h->s_af, np * 16); }
   alloc((void**)&h->d_types, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_wls, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_slot_type, DS_MAX_DRONES_PER_ENV);
@@ -302,6 +310,10 @@ extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, cons
   a.n = h->n; a.n_pad = h->n_pad; a.D = h->cfg.drones_per_env;
   ds_reset_kernel<<<grid_for(h, (h->n_pad + 255) / 256, 8), 256, 0, st>>>(a);
   h->launches++;
+  if (h->ext) {
+    ds_reset_ext_kernel<<<grid_for(h, (h->n_pad + 255) / 256, 8), 256, 0, st>>>(a, h->s_r0, h->s_r1, h->s_af);
+    h->launches++;
+  }
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * DS_NUM_STATS, st));
   {
@@ -327,6 +339,10 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.n = h->n; a.D = h->cfg.drones_per_env; a.tile_v = h->tile_v; a.n_tiles = h->n_tiles;
   a.K = h->cfg.substeps; a.n_types = h->n_types;
   a.rc_kind = h->rc_kind;
+  a.s_r0 = h->s_r0; a.s_r1 = h->s_r1; a.s_af = h->s_af;
+  a.ext = h->ext ? 1 : 0;
+  a.motor_a = h->cfg.motor_tau > 0.f ? (float)(1.0 - exp(-(1.0 / (double)h->cfg.sim_freq) / (double)h->cfg.motor_tau)) : 2.0f;
+  a.acc_b = 2.0f;  // set with the control time step (set_filter)
   a.flags = h->cfg.flags & 0xFu;
   a.dt = 1.0f / h->cfg.sim_freq;
   a.gravity = h->cfg.gravity;
@@ -370,6 +386,10 @@ static void launch_step(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
 
 static int log_sample(ds_handle* h, cudaStream_t st);
 
+static void set_filter(const ds_handle* h, DsArgs& a) {  // b = 1 - exp(-2 pi f_c ctrl_dt)
+  a.acc_b = h->cfg.acc_filter_hz > 0.f ? (float)(1.0 - exp(-2.0 * M_PI * (double)h->cfg.acc_filter_hz * (double)a.ctrl_dt)) : 2.0f;
+}
+
 static void time_flags(const ds_handle* h, DsArgs& a) {
   a.time_hit = (h->cfg.max_steps > 0 && h->step_counter + h->cfg.substeps >= h->cfg.max_steps) ? 1 : 0;
 }
@@ -386,6 +406,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   a.order = order;
   a.ctrl_dt = (float)h->cfg.substeps / h->cfg.sim_freq;  // CTRL_EVERY_N_STEPS * env.TIMESTEP (fly_INDI.py:231)
   a.inv_ctrl_dt = h->cfg.sim_freq / (float)h->cfg.substeps;
+  set_filter(h, a);
   cudaStream_t st = (cudaStream_t)stream;
   for (int i = 0; i < n_control_steps; ++i) {
     a.use_act = (h->first_action_pending && order == 0) ? 1 : 0;
@@ -441,16 +462,18 @@ static int control_common(ds_handle* h, const float* state, const ds_targets* tg
   a.rate_thrust = (const float4*)rate_thrust;
   a.ctrl_dt = control_timestep;
   a.inv_ctrl_dt = 1.0f / control_timestep;
+  set_filter(h, a);
   a.cmd_out = cmd_out; a.pos_e_out = pos_e_out; a.yaw_err_out = yaw_err_out;
   const int grid = grid_for(h, (h->n + DS_TILE - 1) / DS_TILE, 4);
   cudaStream_t st = (cudaStream_t)stream;
-  if (rate_thrust) {
-    if (h->nu6) ds_control_kernel<true, 1><<<grid, DS_TILE, 0, st>>>(a);
-    else ds_control_kernel<false, 1><<<grid, DS_TILE, 0, st>>>(a);
-  } else {
-    if (h->nu6) ds_control_kernel<true, 0><<<grid, DS_TILE, 0, st>>>(a);
-    else ds_control_kernel<false, 0><<<grid, DS_TILE, 0, st>>>(a);
-  }
+#define DS_CTRL(N, M)                                                       \
+  do {                                                                      \
+    if (h->ext) ds_control_kernel<N, M, true><<<grid, DS_TILE, 0, st>>>(a); \
+    else ds_control_kernel<N, M, false><<<grid, DS_TILE, 0, st>>>(a);       \
+  } while (0)
+  if (rate_thrust) { if (h->nu6) DS_CTRL(true, 1); else DS_CTRL(false, 1); }
+  else             { if (h->nu6) DS_CTRL(true, 0); else DS_CTRL(false, 0); }
+#undef DS_CTRL
   h->launches++;
   CK(cudaGetLastError());
   return DS_OK;
@@ -474,7 +497,8 @@ extern "C" int ds_rate_control_step(ds_handle* h, const float* rate_thrust, floa
 
 static void obs_args(const ds_handle* h, DsObsArgs& a) {
   memset(&a, 0, sizeof(a));
-  a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv;
+  a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv; a.s_lr = h->s_lr;
+  a.reward_mode = h->cfg.reward_mode;
   // obs tail = last_clipped_action (BaseAviary.py:787): the external action on the facade path, else the
   // controller command (which is the action the next physics step applies)
   a.s_c0 = h->act_valid ? h->s_a0 : h->s_c0;
@@ -549,6 +573,7 @@ extern "C" int ds_views(ds_handle* h, ds_state_views* out) {
   out->cmd0123 = (float*)h->s_c0; out->cmd45 = (float*)h->s_c1;
   out->slot_type = h->d_slot_type;
   out->step_counter = h->step_counter;
+  out->rpm0123 = (float*)h->s_r0; out->rpm45 = (float*)h->s_r1; out->ang_acc_filt = (float*)h->s_af;
   return DS_OK;
 }
 

@@ -6,7 +6,7 @@
 // ---------------------------------------------------------------------------------------------
 // control only (resident or external state; MODE 1 = rate/thrust entry of RPYTAviary)
 // ---------------------------------------------------------------------------------------------
-template <bool NU6, int MODE>
+template <bool NU6, int MODE, bool EXT>
 __global__ void __launch_bounds__(DS_TILE) ds_control_kernel(const DsArgs a) {
   __shared__ __align__(16) DsTypeDev sh_types[DS_MAX_TYPES_DEV];
   __shared__ uint8_t sh_slot_type[32];
@@ -41,14 +41,15 @@ __global__ void __launch_bounds__(DS_TILE) ds_control_kernel(const DsArgs a) {
     if (NU6) { float2 C1 = a.s_c1[v]; m.cmd[4] = C1.x; m.cmd[5] = C1.y; } else { m.cmd[4] = m.cmd[5] = 0.f; }
     CtrlOut o = {0.f, 0.f, 0.f, 0.f, 0, 0};
     int wp = __float_as_int(W.w);
+    if (EXT) { const float4 AF = a.s_af[v]; m.afx = AF.x; m.afy = AF.y; m.afz = AF.z; }
     if (MODE == 0) {
       const float4* tg = ds_staged_target(a);
       CtrlTarget t = ds_fetch_target(a, tp, cs, v, wp, tg ? tg + v : nullptr);
-      ds_indi_control<NU6>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, m, o, true);
+      ds_indi_control<NU6, EXT>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, a.acc_b, m, o, true);
     } else {  // INDIControl._INDIRateControl (INDIControl.py:413-490)
       float4 rt = a.rate_thrust[v];
       float nu[4];
-      ds_rate_loop(tp, cs, a.inv_ctrl_dt, rt.x, rt.y, rt.z, m, nu);
+      ds_rate_loop<EXT>(tp, cs, a.inv_ctrl_dt, a.acc_b, rt.x, rt.y, rt.z, m, nu);
       nu[3] = rt.w - m.lthrust;
       m.lthrust = rt.w;
       ds_allocate_quad<NU6>(tp, nu, m, o);
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(DS_TILE) ds_control_kernel(const DsArgs a) {
     a.s_lr[v] = make_float4(m.lrx, m.lry, m.lrz, sqrtf(o.pex * o.pex + o.pey * o.pey + o.pez * o.pez));
     a.s_c0[v] = make_float4(m.cmd[0], m.cmd[1], m.cmd[2], m.cmd[3]);
     if (NU6) a.s_c1[v] = make_float2(m.cmd[4], m.cmd[5]);
+    if (EXT) a.s_af[v] = make_float4(m.afx, m.afy, m.afz, 0.f);
     if (a.cmd_out) {
       float* c = a.cmd_out + (size_t)v * 6;
 #pragma unroll
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(DS_TILE) ds_control_kernel(const DsArgs a) {
 // observation (CtrlAviary._computeObs, CtrlAviary.py:212-232)
 // ---------------------------------------------------------------------------------------------
 struct DsObsArgs {
-  const float4 *s_pos, *s_quat, *s_vel, *s_om, *s_lv, *s_c0;
+  const float4 *s_pos, *s_quat, *s_vel, *s_om, *s_lv, *s_lr, *s_c0;
   const float2* s_c1;
   const uint8_t* slot_type;
   const DsTypeDev* types;
@@ -82,6 +84,7 @@ struct DsObsArgs {
   uint8_t* done_env;
   float* reward_env;
   int n, D, nu6;
+  int reward_mode;  // 0: constant -1 (the reference); 1: -mean |pos_e| of the env
   float radius;
 };
 
@@ -132,7 +135,15 @@ __global__ void __launch_bounds__(256) ds_obs_kernel(const DsObsArgs a) {
         any |= (j == 0) ? b : (b & 6u);
       }
       if (a.done_env) a.done_env[v / a.D] = any ? 1 : 0;
-      if (a.reward_env) a.reward_env[v / a.D] = -1.0f;  // CtrlAviary.py:267-278
+      if (a.reward_env) {
+        float rw = -1.0f;  // CtrlAviary.py:267-278
+        if (a.reward_mode == 1) {  // extension: minus the env's mean position error of the last control step
+          float sum = 0.f;
+          for (int j = 0; j < a.D; ++j) sum += a.s_lr[env0 + j].w;
+          rw = -sum / (float)a.D;
+        }
+        a.reward_env[v / a.D] = rw;
+      }
     }
   }
 }
@@ -199,6 +210,20 @@ __global__ void __launch_bounds__(256) ds_reset_kernel(const DsResetArgs a) {
       for (int i = 0; i < 6; ++i) ac[i] = (i < nu) ? a.action0[6 * v + i] : 0.f;
     a.s_a0[v] = make_float4(ac[0], ac[1], ac[2], ac[3]);
     a.s_a1[v] = make_float2(ac[4], ac[5]);
+  }
+}
+
+// extension state after reset: rotor speeds of the all-zero action, filter state zero
+__global__ void __launch_bounds__(256) ds_reset_ext_kernel(const DsResetArgs a, float4* s_r0, float2* s_r1, float4* s_af) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n_pad; v += gridDim.x * blockDim.x) {
+    float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (v < a.n) {
+      const DsTypeDev& tp = a.types[a.slot_type[v % a.D]];
+      for (int i = 0; i < tp.n_u; ++i) r[i] = tp.rotor[i].cnst;  // last_clipped_action = 0 after reset (BaseAviary.py:659-662)
+    }
+    s_r0[v] = make_float4(r[0], r[1], r[2], r[3]);
+    s_r1[v] = make_float2(r[4], r[5]);
+    s_af[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

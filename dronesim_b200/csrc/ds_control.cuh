@@ -21,7 +21,7 @@ struct CtrlState {   // kinematic state the controller sees
   float wx, wy, wz;  // BODY rates (the reference rotates the world rates first, INDIControl.py:428-430)
 };
 struct CtrlTarget { float x, y, z, yaw, vx, vy, vz, ax, ay, az; };
-struct CtrlMem { float lvx, lvy, lvz, lrx, lry, lrz, lthrust; float cmd[6]; };
+struct CtrlMem { float lvx, lvy, lvz, lrx, lry, lrz, lthrust; float cmd[6]; float afx, afy, afz; };
 struct CtrlOut { float pex, pey, pez, yaw_err; int wls_iter; int sat; };
 
 template <bool NU6>
@@ -40,19 +40,28 @@ __device__ __forceinline__ void ds_allocate_quad(const DsTypeDev& tp, const floa
   }
 }
 
-// rate loop shared by both laws: returns nu[0..2] and updates last_rates (INDIControl.py:428-453)
-__device__ __forceinline__ void ds_rate_loop(const DsTypeDev& tp, const CtrlState& s, float inv_dt, float rsp_p,
+// rate loop shared by both laws: returns nu[0..2] and updates last_rates (INDIControl.py:428-453).
+// EXT: first-order low-pass on the angular-acceleration estimate (north_star; the reference's filter is a commented
+// placeholder, INDIControl.py:432-439): a_f += b (a_raw - a_f), b >= 1 = off.
+template <bool EXT>
+__device__ __forceinline__ void ds_rate_loop(const DsTypeDev& tp, const CtrlState& s, float inv_dt, float acc_b, float rsp_p,
                                              float rsp_q, float rsp_r, CtrlMem& m, float nu[3]) {
   float aax = (s.wx - m.lrx) * inv_dt, aay = (s.wy - m.lry) * inv_dt, aaz = (s.wz - m.lrz) * inv_dt;
   m.lrx = s.wx; m.lry = s.wy; m.lrz = s.wz;
+  if (EXT) {
+    if (acc_b < 1.f) {
+      aax = fmaf(acc_b, aax - m.afx, m.afx); aay = fmaf(acc_b, aay - m.afy, m.afy); aaz = fmaf(acc_b, aaz - m.afz, m.afz);
+    }
+    m.afx = aax; m.afy = aay; m.afz = aaz;
+  }
   nu[0] = (rsp_p - s.wx) * tp.rate[0] - aax;
   nu[1] = (rsp_q - s.wy) * tp.rate[1] - aay;
   nu[2] = (rsp_r - s.wz) * tp.rate[2] - aaz;
 }
 
-template <bool NU6>
+template <bool NU6, bool EXT>
 __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWlsDev* __restrict__ wls_tab, int type_id,
-                                                const CtrlState& s, const CtrlTarget& t, float inv_dt, CtrlMem& m,
+                                                const CtrlState& s, const CtrlTarget& t, float inv_dt, float acc_b, CtrlMem& m,
                                                 CtrlOut& o, bool want_yaw_err) {
   // ---- position loop (INDIControl.py:278-296 / INDIControl_6DOF.py:390-413)
   o.pex = t.x - s.px; o.pey = t.y - s.py; o.pez = t.z - s.pz;
@@ -116,7 +125,7 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
     float ez = w * tq.z - x * tq.y + y * tq.x - z * tq.w;
     if (ew < 0.f) { ex = -ex; ey = -ey; ez = -ez; }  // quat_wrap_shortest, in place (quirk Q1)
     float nu[4];
-    ds_rate_loop(tp, s, inv_dt, tp.att[0] * ex, tp.att[1] * ey, tp.att[2] * ez, m, nu);
+    ds_rate_loop<EXT>(tp, s, inv_dt, acc_b, tp.att[0] * ex, tp.att[1] * ey, tp.att[2] * ez, m, nu);
     nu[3] = dT;  // thrust - last_thrust (:454); dT avoids the FP32 cancellation of (lt + dT) - lt
     m.lthrust = thrust;
     ds_allocate_quad<NU6>(tp, nu, m, o);
@@ -128,7 +137,7 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
       float r0 = cpsi * e0 + spsi * e1;  // inv(R_psi) (:551-557)
       float r1 = -spsi * e0 + cpsi * e1;
       float nu[6];
-      ds_rate_loop(tp, s, inv_dt, tp.att[0] * r0, tp.att[1] * r1, tp.att[2] * e2, m, nu);
+      ds_rate_loop<EXT>(tp, s, inv_dt, acc_b, tp.att[0] * r0, tp.att[1] * r1, tp.att[2] * e2, m, nu);
       // accel_error_body = R^T accel_e (:589) - uses the quaternion's own matrix, not the Euler one
       nu[3] = R.m00 * aex + R.m10 * aey + R.m20 * aez;
       nu[4] = R.m01 * aex + R.m11 * aey + R.m21 * aez;

@@ -72,6 +72,10 @@ struct DsArgs {
   float2* s_c1;    // controller cmd 4..5
   float4* s_a0;    // last clipped action 0..3 (facade path / first step after reset)
   float2* s_a1;
+  // extension state (north_star items beyond the reference; allocated only when enabled)
+  float4* s_r0;    // actual rotor speed 0..3 (first-order motor model)
+  float2* s_r1;    // actual rotor speed 4..5
+  float4* s_af;    // filtered angular-acceleration estimate x y z | -
   const DsTypeDev* types;
   const DsWlsDev* wls;
   const uint8_t* slot_type;
@@ -90,6 +94,9 @@ struct DsArgs {
   float dt;         // TIMESTEP
   float gravity;
   float ctrl_dt, inv_ctrl_dt;
+  int ext;          // 1: the EXT kernel variant runs (motor model and / or angular-acceleration filter on)
+  float motor_a;    // 1 - exp(-dt / tau_motor); >= 1: static map (BaseAviary.py:1487-1490)
+  float acc_b;      // 1 - exp(-2 pi f_c ctrl_dt); >= 1: raw finite difference (INDIControl.py:432-439)
   // targets
   int tmode, num_wp, advance_wp;
   const float4* t_pos;

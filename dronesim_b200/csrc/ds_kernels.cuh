@@ -1,6 +1,6 @@
 // Kernels of the dronesim_b200 core.
 //
-//  ds_step_kernel<INTEG, DW, NU6, WARPSYNC, MODE, FX>
+//  ds_step_kernel<INTEG, DW, NU6, WARPSYNC, MODE, FX, EXT>
 //      MODE 0 (fused): K physics substeps + one INDI evaluation per vehicle  (examples/fly_INDI.py:217-245)
 //      MODE 1 (physics only): BaseAviary.step with an external action        (BaseAviary.py:428-555)
 //  ds_control_kernel<NU6>      INDIControl.computeControl on resident or external state
@@ -177,7 +177,7 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsT
   return t;
 }
 
-template <int INTEG, int DW, bool NU6, bool WARPSYNC, int MODE, int FX>
+template <int INTEG, int DW, bool NU6, bool WARPSYNC, int MODE, int FX, bool EXT>
 __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsArgs a) {
   extern __shared__ __align__(128) unsigned char ds_stage_mem[];  // 2 x ds_stage_bytes<MODE>()
   __shared__ __align__(8) unsigned long long sh_bar[2];  // per stage: the stage's bulk copies have landed
@@ -251,18 +251,19 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
         m.cmd[4] = m.cmd[5] = 0.f;
       }
       done_bits = __float_as_uint(LV.w);
+      if (EXT) { const float4 AF = a.s_af[vv]; m.afx = AF.x; m.afy = AF.y; m.afz = AF.z; }
       CtrlState cs = {s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, s.wx, s.wy, s.wz};
       const float4* tg0 = sg + SG_TG * T + ld;
       if (a.tmode == 3) {  // RPYTAviary._preprocessAction -> INDIControl._INDIRateControl (RPYTAviary.py:180-193)
         const float4 rt = *tg0;
         float nu[4];
-        ds_rate_loop(tp, cs, a.inv_ctrl_dt, rt.x, rt.y, rt.z, m, nu);
+        ds_rate_loop<EXT>(tp, cs, a.inv_ctrl_dt, a.acc_b, rt.x, rt.y, rt.z, m, nu);
         nu[3] = rt.w - m.lthrust;  // INDIControl.py:454
         m.lthrust = rt.w;
         ds_allocate_quad<NU6>(tp, nu, m, o);
       } else {
         CtrlTarget t = ds_fetch_target(a, tp, cs, vv, wp, tg0);
-        ds_indi_control<NU6>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, m, o, false);
+        ds_indi_control<NU6, EXT>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, a.acc_b, m, o, false);
       }
       perr = sqrtf(o.pex * o.pex + o.pey * o.pey + o.pez * o.pez);
       lthrust = m.lthrust;
@@ -294,7 +295,13 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
       }
     }
 
-    ds_physics<INTEG, DW, NU6, WARPSYNC, FX>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum);
+    float rpm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actual rotor speeds (motor model, EXT only)
+    if (EXT) {
+      const float4 R0 = a.s_r0[vv];
+      rpm[0] = R0.x; rpm[1] = R0.y; rpm[2] = R0.z; rpm[3] = R0.w;
+      if (NU6) { const float2 R1 = a.s_r1[vv]; rpm[4] = R1.x; rpm[5] = R1.y; }
+    }
+    ds_physics<INTEG, DW, NU6, WARPSYNC, FX, EXT>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum, rpm);
     if (MODE == 0 && a.order == 0) control();
     if (MODE == 1) done_bits = __float_as_uint(sg[SG_LV * T + ld].w);
 
@@ -311,6 +318,11 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
       a.s_quat[v] = make_float4(s.qx, s.qy, s.qz, s.qw);
       a.s_vel[v] = make_float4(s.vx, s.vy, s.vz, prev_rpm_sum);
       a.s_om[v] = make_float4(s.wx, s.wy, s.wz, __int_as_float(wp));
+      if (EXT) {
+        a.s_r0[v] = make_float4(rpm[0], rpm[1], rpm[2], rpm[3]);
+        if (NU6) a.s_r1[v] = make_float2(rpm[4], rpm[5]);
+        if (MODE == 0) a.s_af[v] = make_float4(m.afx, m.afy, m.afz, 0.f);
+      }
       if (MODE == 0) {
         a.s_lv[v] = make_float4(m.lvx, m.lvy, m.lvz, __uint_as_float(done_bits));
         a.s_lr[v] = make_float4(m.lrx, m.lry, m.lrz, perr);

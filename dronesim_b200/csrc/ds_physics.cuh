@@ -157,9 +157,11 @@ __device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict_
 // state is integrated at the centre of mass, the add-ons that the reference applies at the base-frame
 // origin (drag, downwash: R7 of oracle/dynamics.py) see p_base = c - R rc, v_base = u - R (w x rc) and add the
 // torque (-rc) x f.
-template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX>
+// EXT: first-order motor model (north_star; R9 of oracle/dynamics.py): rpm[] holds the actual rotor speeds (in / out),
+// every substep moves them towards the commanded speed and rebuilds the rotor wrench, so nothing is hoisted.
+template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX, bool EXT>
 __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_row0, int my_row, float4* sh_pos,
-                                           const float* act, PhysState& s, float& prev_rpm_sum) {
+                                           const float* act, PhysState& s, float& prev_rpm_sum, float* rpm_state) {
   constexpr int NU = NU6 ? 6 : 4;
   const float dt = a.dt;
   const bool gnd = (FX >= 0) ? ((FX & 1) != 0) : ((a.flags & 1u) != 0);
@@ -171,19 +173,28 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   const bool has_rc = rc_kind != 0;
   const bool rc_gen = rc_kind == 1;
 
-  // ---- per control step: rotor thrusts and the constant part of the body wrench
+  // ---- rotor thrusts and the rotor part of the body wrench: once per control step (the command is constant across
+  // the substeps), or once per substep when the motor model moves the rotor speeds
   float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
   float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
+  auto rotor_wrench = [&]() {
+    rpm_sum = 0.f; F0x = 0.f; F0y = 0.f; F0z = 0.f; t0x = 0.f; t0y = 0.f; t0z = 0.f;
 #pragma unroll
-  for (int i = 0; i < NU; ++i) {  // rotors beyond n_u have scale = const = 0 -> T = 0
-    const DsRotorDev& r = tp.rotor[i];
-    float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
-    rpm_sum += rpm;
-    float T = tp.kf * rpm * rpm;                // :1515
-    Tg[i] = T * tp.gnd_k;
-    F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
-    t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
-  }
+    for (int i = 0; i < NU; ++i) {  // rotors beyond n_u have scale = const = 0 -> T = 0
+      const DsRotorDev& r = tp.rotor[i];
+      float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
+      if (EXT) {
+        rpm = (a.motor_a >= 1.f) ? rpm : fmaf(a.motor_a, rpm - rpm_state[i], rpm_state[i]);
+        rpm_state[i] = rpm;
+      }
+      rpm_sum += rpm;
+      float T = tp.kf * rpm * rpm;                // :1515
+      Tg[i] = T * tp.gnd_k;
+      F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
+      t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
+    }
+  };
+  if (!EXT) rotor_wrench();
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
 
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
@@ -222,6 +233,10 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   const float dk0 = -tp.drag_k[0], dk1 = -tp.drag_k[1], dk2 = -tp.drag_k[2];
 
   for (int k = 0; k < a.K; ++k) {
+    if (EXT) {  // drag sees the rotor speeds before this substep's motor update
+      if (k > 0) prev_rpm_sum = rpm_sum;
+      rotor_wrench();
+    }
     // ---- downwash first (BaseAviary.py:1747-1763): it needs the base-frame origin only, so the rotation matrix
     // does not have to stay live (or be rematerialised) across the unrolled pair loop
     float dw_fz = 0.f;
@@ -275,7 +290,7 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
         rot_wxrc(R, ox, oy, oz);
         vx -= ox; vy -= oy; vz -= oz;
       }
-      const float sum = (k == 0) ? prev_rpm_sum : rpm_sum;
+      const float sum = (EXT || k == 0) ? prev_rpm_sum : rpm_sum;
       float d0 = (dk0 * sum) * vx, d1 = (dk1 * sum) * vy, d2 = (dk2 * sum) * vz;
       float fx = R.m00 * d0 + R.m01 * d1 + R.m02 * d2;
       float fy = R.m10 * d0 + R.m11 * d1 + R.m12 * d2;

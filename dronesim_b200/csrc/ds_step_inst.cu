@@ -22,19 +22,23 @@ static void launch4(const DsArgs& a, int grid, cudaStream_t st) {
   KERNEL<<<grid, DS_TILE, kSmem, st>>>(a);
 }
 
-template <int DW, bool NU6, int FX>
+template <int DW, bool NU6, int FX, bool EXT>
 static void launch3(bool warpsync, const DsArgs& a, int grid, cudaStream_t st) {
   // warp-level sync of the downwash snapshot needs every env inside one warp: D | 32 (always true of the D = 16 variant)
-  if (DW == 2 || warpsync) launch4<ds_step_kernel<DS_INST_INTEG, DW, NU6, true, DS_INST_MODE, FX>>(a, grid, st);
-  else launch4<ds_step_kernel<DS_INST_INTEG, (DW == 2 ? 1 : DW), NU6, false, DS_INST_MODE, FX>>(a, grid, st);
+  if (DW == 2 || warpsync) launch4<ds_step_kernel<DS_INST_INTEG, DW, NU6, true, DS_INST_MODE, FX, EXT>>(a, grid, st);
+  else launch4<ds_step_kernel<DS_INST_INTEG, (DW == 2 ? 1 : DW), NU6, false, DS_INST_MODE, FX, EXT>>(a, grid, st);
 }
 
 template <int DW, bool NU6>
 static void launch2(bool warpsync, const DsArgs& a, int grid, cudaStream_t st) {
   // FX: ground effect + drag resolved at compile time for the all-add-ons configuration (straight-line substep body),
   // run-time flags otherwise
-  if (DW != 0 && (a.flags & 3u) == 3u) launch3<DW, NU6, 3>(warpsync, a, grid, st);
-  else launch3<DW, NU6, -1>(warpsync, a, grid, st);
+#if DS_INST_INTEG == 0
+  // EXT: motor model / angular-acceleration filter (extensions beyond the reference; quaternion integrator only)
+  if (a.ext) { launch3<DW, NU6, -1, true>(warpsync, a, grid, st); return; }
+#endif
+  if (DW != 0 && (a.flags & 3u) == 3u) launch3<DW, NU6, 3, false>(warpsync, a, grid, st);
+  else launch3<DW, NU6, -1, false>(warpsync, a, grid, st);
 }
 
 #define DS_CONCAT3_(a, b, c) a##b##_##c

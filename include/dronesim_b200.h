@@ -84,6 +84,13 @@ typedef struct ds_config {
   float z_min;
   int32_t max_steps;       /* DS_DONE_TIME when step_counter >= max_steps; 0 = off */
   int32_t env_offset;      /* global index of this shard's first env (multi-GPU bookkeeping only) */
+  /* Extensions the north_star asks for beyond the reference; 0 = off = the reference's behaviour.  Quaternion
+   * integrator only (DS_ERR_UNSUPPORTED with DS_INTEG_RPY). */
+  float motor_tau;         /* s: first-order motor model, rpm += (1 - exp(-dt / tau)) (rpm_cmd - rpm) every substep;
+                              0 = the static PWM -> RPM map (BaseAviary.py:1487-1490) */
+  float acc_filter_hz;     /* Hz: first-order low-pass on the INDI angular-acceleration estimate; 0 = the raw finite
+                              difference (the reference's filter is a commented placeholder, INDIControl.py:432-439) */
+  int32_t reward_mode;     /* 0: constant -1 (CtrlAviary.py:267-278); 1: minus the env's mean |pos_e| of the last control step */
 } ds_config;
 
 /* Per-type constants.  Field sources: BaseAviary._parseURDFParameters (BaseAviary.py:2041-2140),
@@ -152,6 +159,9 @@ typedef struct ds_state_views {
   float* cmd45;          /* [n_pad][2] rotors 4,5 */
   uint8_t* slot_type;    /* [drones_per_env] type id of each slot */
   int64_t step_counter;  /* BaseAviary.step_counter (BaseAviary.py:554) */
+  float* rpm0123;        /* [n_pad][4] actual rotor speeds 0..3 (motor model on) or NULL */
+  float* rpm45;          /* [n_pad][2] or NULL */
+  float* ang_acc_filt;   /* [n_pad][4] filtered angular acceleration x,y,z (filter or motor model on) or NULL */
 } ds_state_views;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */

@@ -195,7 +195,17 @@ class _Base:
         self.rate = np.array(vt.rate_gain, dtype=float)
         self.MIN_PWM = np.array(vt.MIN_PWM, dtype=float)
         self.MAX_PWM = np.array(vt.MAX_PWM, dtype=float)
+        # extension beyond the reference (its filter is a commented placeholder, INDIControl.py:432-439):
+        # first-order low-pass on the angular-acceleration estimate, coefficient b per control step; None = off
+        self.acc_b = None
+        self.ang_acc_filt = np.zeros(3)
         self.reset()
+
+    def _filter_ang_acc(self, angular_accel):
+        if self.acc_b is None:
+            return angular_accel
+        self.ang_acc_filt = self.ang_acc_filt + self.acc_b * (angular_accel - self.ang_acc_filt)
+        return self.ang_acc_filt.copy()
 
     def computeControlFromState(self, control_timestep, state, target_pos, target_vel=np.zeros(3),
                                 target_acc=np.zeros(3), target_rpy=np.zeros(3), target_rpy_rates=np.zeros(3)):
@@ -219,6 +229,7 @@ class QuadINDI(_Base):
         self.last_thrust = 0.0
         self.cmd = np.ones(self.n_u) * 0.0
         self.last_vel = np.zeros(3)
+        self.ang_acc_filt = np.zeros(3)
 
     def computeControl(self, control_timestep, cur_pos, cur_quat, cur_vel, cur_ang_vel, target_pos,
                        target_vel=np.zeros(3), target_acc=np.zeros(3), target_rpy=np.zeros(3),
@@ -255,7 +266,7 @@ class QuadINDI(_Base):
         """INDIControl._INDIRateControl (INDIControl.py:413-490); also the RPYTAviary entry."""
         R = p.rotmat(cur_quat)
         w = R.T.dot(cur_ang_vel)
-        angular_accel = (w - self.last_rates) / (1.0 * dt)
+        angular_accel = self._filter_ang_acc((w - self.last_rates) / (1.0 * dt))
         self.last_rates = w
         indi_v = np.zeros(4)
         indi_v[0:3] = (np.asarray(rate_sp) - w) * self.rate - angular_accel
@@ -277,6 +288,7 @@ class Hexa6DOFINDI(_Base):
         self.last_thrust = 0.3
         self.cmd = np.ones(self.n_u) * 0.5
         self.last_vel = np.zeros(3)
+        self.ang_acc_filt = np.zeros(3)
         self.wls_fail = 0
         self.last_wls_iter = 0
 
@@ -309,7 +321,7 @@ class Hexa6DOFINDI(_Base):
         rate_sp = self.att * att_err
         R = p.rotmat(cur_quat)
         w = R.T.dot(cur_ang_vel)
-        angular_accel = (w - self.last_rates) / (1.0 * dt)
+        angular_accel = self._filter_ang_acc((w - self.last_rates) / (1.0 * dt))
         self.last_rates = w
         indi_v = np.zeros(6)
         indi_v[0:3] = (rate_sp - w) * self.rate - angular_accel

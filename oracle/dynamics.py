@@ -35,6 +35,9 @@ R7  ``_drag`` / ``_downwash`` forces act at the base-frame origin along LINK_FRA
     RECEIVING drone's coefficients.
 R8  integrator ``"quat"`` (beyond the reference, asked by north_star): Newton-Euler about the
     composite centre of mass, semi-implicit Euler, exponential-map quaternion update.
+R9  first-order motor model (beyond the reference, asked by north_star; off by default): per substep
+    rpm += (1 - exp(-dt / tau)) (rpm_cmd - rpm); thrust / torque / ground effect use the actual rpm, drag the
+    actual rpm sum before the substep's update.  tau = 0 is the reference's static map (:1487-1490).
 """
 import math
 
@@ -100,10 +103,11 @@ def quat_exp(w, dt):
     return np.array([th[0] * k, th[1] * k, th[2] * k, math.cos(half)])
 
 
-def body_wrench(pp, cmd, cmd_prev_rpm_sum, pos, quat, rpy, vel, others_pos, gnd, drag, dw):
-    """Body-frame force and torque about the (composite) centre of mass for one substep."""
+def body_wrench(pp, cmd, cmd_prev_rpm_sum, pos, quat, rpy, vel, others_pos, gnd, drag, dw, rpm=None):
+    """Body-frame force and torque about the (composite) centre of mass for one substep.
+    ``rpm``: actual rotor speeds when the first-order motor model (extension, R9) is on; default = the static map."""
     R = p.rotmat(quat)
-    rpm = rpm_of_cmd(pp, cmd)
+    rpm = rpm_of_cmd(pp, cmd) if rpm is None else np.asarray(rpm, float)
     T = pp.kf * rpm**2  # :1515 / :1402
     Q = pp.km * rpm**2  # :1516 / :1403
     F = np.zeros(3)

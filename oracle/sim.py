@@ -14,6 +14,8 @@ Integer work restated bit-exactly: waypoint counter (above), ``step_counter += A
 (BaseAviary.py:554), adjacency ``||p_i - p_j|| < R`` strict (BaseAviary.py:913-921), and the
 batched ``done`` predicate built on ``fly_INDI_TrajectoryTrack.py:249-250``.
 """
+import math
+
 import numpy as np
 
 from . import control as oc
@@ -27,7 +29,8 @@ DONE_TIME = 4  # step_counter >= max_steps     (beyond the reference; off by def
 
 class OracleSwarm:
     def __init__(self, slot_types, n_envs, integrator="quat", composite=True, gnd=False, drag=False,
-                 dw=False, freq=240, aggregate_phy_steps=1, neighbourhood_radius=np.inf):
+                 dw=False, freq=240, aggregate_phy_steps=1, neighbourhood_radius=np.inf, motor_tau=0.0,
+                 acc_filter_hz=0.0):
         """``slot_types``: list of VehicleType, one per drone slot of an env (the reference's
         ``drone_model`` list, BaseAviary.py:131,219); every env has the same slot->type map."""
         self.E, self.D = int(n_envs), len(slot_types)
@@ -41,6 +44,15 @@ class OracleSwarm:
         self.radius = neighbourhood_radius
         self.n_u = [vt.INDI_ACTUATOR_NR for vt in self.types]
         self.ctrl = [[oc.make_controller(vt) for vt in self.types] for _ in range(self.E)]
+        # extensions beyond the reference (north_star), off by default: first-order motor lag (time constant, s)
+        # and a first-order low-pass (cut-off, Hz) on the controllers' angular-acceleration estimate
+        self.motor_tau = float(motor_tau)
+        self.motor_a = 1.0 - math.exp(-self.TIMESTEP / self.motor_tau) if self.motor_tau > 0 else None
+        if acc_filter_hz > 0:
+            b = 1.0 - math.exp(-2.0 * math.pi * float(acc_filter_hz) * self.K * self.TIMESTEP)
+            for row in self.ctrl:
+                for c in row:
+                    c.acc_b = b
         self.goal = None
         self.goal_radius = 0.3
         self.z_min = None
@@ -60,6 +72,9 @@ class OracleSwarm:
         self.vel = np.zeros((E, D, 3)) if vel0 is None else np.array(vel0, float).reshape(E, D, 3).copy()
         self.rates = np.zeros((E, D, 3))  # body rates
         self.last_clipped_action = np.zeros((E, D, 6))  # BaseAviary.py:659-662
+        self.rpm = np.zeros((E, D, 6))  # motor model state: starts at the rpm of the all-zero action
+        for d in range(D):
+            self.rpm[:, d, : self.n_u[d]] = od.rpm_of_cmd(self.pp[d], np.zeros(self.n_u[d]))
         self.step_counter = 0
         self.done_bits = np.zeros((E, D), dtype=np.uint8)
         for e in range(E):
@@ -104,8 +119,13 @@ class OracleSwarm:
                     n, pp = self.n_u[d], self.pp[d]
                     prev_sum = float(np.sum(od.rpm_of_cmd(pp, self.last_clipped_action[e, d, :n])))
                     others = [snap_pos[j] for j in range(self.D) if j != d] if self.dw else []
+                    rpm = None
+                    if self.motor_a is not None:  # R9: first-order lag towards the commanded rpm
+                        prev_sum = float(np.sum(self.rpm[e, d, :n]))
+                        self.rpm[e, d, :n] += self.motor_a * (od.rpm_of_cmd(pp, clipped[d, :n]) - self.rpm[e, d, :n])
+                        rpm = self.rpm[e, d, :n]
                     F, tau, R = od.body_wrench(pp, clipped[d, :n], prev_sum, snap_pos[d], self.quat[e, d],
-                                               self.rpy[e, d], self.vel[e, d], others, self.gnd, self.drag, self.dw)
+                                               self.rpy[e, d], self.vel[e, d], others, self.gnd, self.drag, self.dw, rpm=rpm)
                     if self.integrator == "rpy":
                         new.append(od.substep_rpy(pp, dt, snap_pos[d], self.quat[e, d], self.rpy[e, d],
                                                   self.vel[e, d], self.rates[e, d], F, tau, R))

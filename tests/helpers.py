@@ -17,7 +17,8 @@ def angle_between(q1, q2):
     return 2.0 * np.arccos(np.clip(d, -1.0, 1.0))
 
 
-def make_pair(models, n_envs, integrator, K, gnd=False, drag=False, dw=False, radius=np.inf, **kw):
+def make_pair(models, n_envs, integrator, K, gnd=False, drag=False, dw=False, radius=np.inf, motor_tau=0.0, acc_filter_hz=0.0,
+              **kw):
     """(SwarmCore, OracleSwarm) with identical configuration."""
     from dronesim_b200.core import SwarmCore
     from dronesim_b200.vehicles import load_vehicle
@@ -25,9 +26,9 @@ def make_pair(models, n_envs, integrator, K, gnd=False, drag=False, dw=False, ra
     vts = [load_vehicle(m) for m in models]
     composite = integrator == "quat"
     core = SwarmCore(vts, n_envs, integrator=integrator, composite=composite, ground=gnd, drag=drag, downwash=dw,
-                     aggregate_phy_steps=K, neighbourhood_radius=radius, **kw)
+                     aggregate_phy_steps=K, neighbourhood_radius=radius, motor_tau=motor_tau, acc_filter_hz=acc_filter_hz, **kw)
     orc = OracleSwarm(vts, n_envs, integrator=integrator, composite=composite, gnd=gnd, drag=drag, dw=dw,
-                      aggregate_phy_steps=K, neighbourhood_radius=radius)
+                      aggregate_phy_steps=K, neighbourhood_radius=radius, motor_tau=motor_tau, acc_filter_hz=acc_filter_hz)
     return core, orc
 
 

@@ -502,3 +502,46 @@ def test_dynamics_substep_vs_reference_fixture(name):
     np.testing.assert_allclose(st["omega_body"], g["dyn_rates"], rtol=2e-5, atol=2e-4)
     assert angle_between(st["quat"], g["dyn_quat"]).max() <= 2e-6
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# north_star extensions beyond the reference (off by default): first-order motor model, low-passed angular
+# acceleration, tracking reward - against the oracle's restatement of the same definitions (parity unpinned:
+# the reference has a static motor map and a commented-out filter)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("motor_tau,acc_hz", [(0.05, 0.0), (0.0, 15.0), (0.03, 25.0)])
+def test_extensions_motor_model_and_acc_filter(motor_tau, acc_hz):
+    _need_gpu()
+    models = ["robobee", "hexa_6DOF", "tello", "hexa_6DOF_simple"]
+    D, E, K = 4, 3, 4
+    core, orc = make_pair(models, E, "quat", K=K, gnd=True, drag=True, dw=True, motor_tau=motor_tau, acc_filter_hz=acc_hz,
+                          reward_mode=1)
+    rng = np.random.default_rng(21)
+    pos0 = np.zeros((E, D, 3))
+    for s_ in range(D):
+        pos0[:, s_] = [1.5 * s_, 0.0, 2.0 + 0.3 * (s_ % 2)]
+    pos0 += rng.uniform(-0.02, 0.02, pos0.shape)
+    act0 = np.zeros((E, D, 6))
+    for s_, m in enumerate(models):
+        act0[:, s_, : (6 if "hexa" in m else 4)] = 0.45
+    tyaw = rng.uniform(-0.3, 0.3, (E, D))
+    core.reset(pos0, action0=act0)
+    orc.reset(pos0)
+    tgt = core.targets_per_vehicle(np.concatenate([pos0.reshape(-1, 3), tyaw.reshape(-1, 1)], axis=1))
+    act = act0.copy()
+    for step in range(60):  # 60 control steps x 4 substeps = 1 s
+        core.step(tgt, 1)
+        orc.physics_step(act)
+        act = orc.control_step(pos0, tyaw=tyaw)
+    _compare_state(core, orc, what="ext tau=%g hz=%g" % (motor_tau, acc_hz))
+    v = core.views()
+    if motor_tau > 0:
+        np.testing.assert_allclose(v["rpm"].cpu().numpy().reshape(E, D, 6), orc.rpm, rtol=2e-5, atol=0.5)
+    if acc_hz > 0:
+        ref = np.array([[orc.ctrl[e][d].ang_acc_filt for d in range(D)] for e in range(E)])
+        np.testing.assert_allclose(v["ang_acc_filt"].cpu().numpy().reshape(E, D, 3), ref, atol=5e-3)
+    # tracking reward: minus the env's mean |pos_e| of the last control step, reduced on the device
+    _, _, _, rw = core.get_obs(state=False, neighbors=False, done=False, reward=True)
+    exp = -np.linalg.norm(orc.pos_e, axis=2).mean(axis=1)
+    np.testing.assert_allclose(rw.cpu().numpy(), exp, atol=2e-4)
+    core.close()

@@ -83,7 +83,9 @@ def test_device_log_equals_per_step_observations():
         seen.append(obs["state"][2].cpu().numpy().astype(np.float64))  # [2, 22] of env 2
     T = lg.collect()
     assert T == 30 and lg.states.shape == (2, 22, 30)
-    np.testing.assert_array_equal(lg.states, np.stack(seen, axis=2))  # same kernel arithmetic: bit-exact
+    # same device function in two kernels (ds_log_kernel / ds_obs_kernel): equal up to FMA-contraction choices
+    np.testing.assert_allclose(lg.states, np.stack(seen, axis=2), rtol=5e-7, atol=2e-7)
+    np.testing.assert_array_equal(lg.states[:, 0:7], np.stack(seen, axis=2)[:, 0:7])  # copied fields are bit-exact
     np.testing.assert_allclose(lg.timestamps[0], (np.arange(30) + 1) * 5 / 240.0)
     # a second reset rewinds the device log
     env.reset()

@@ -545,3 +545,72 @@ def test_extensions_motor_model_and_acc_filter(motor_tau, acc_hz):
     exp = -np.linalg.norm(orc.pos_e, axis=2).mean(axis=1)
     np.testing.assert_allclose(rw.cpu().numpy(), exp, atol=2e-4)
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes, through size-independent properties (the FP64 Python oracle cannot step a million
+# vehicles): an env's trajectory does not depend on how many other envs share the launch or where its tile falls
+# (bit-exact against a small run the oracle-checked tests above cover), identical envs stay identical, integer
+# bookkeeping has a closed form, nothing goes non-finite
+# ------------------------------------------------------------------------------------------
+def test_full_size_hetero_swarm_properties():
+    """configs[3]: 65,536 envs x 16 drones = 1,048,576 vehicles, ground + drag + downwash, K = 8."""
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.workloads import hetero16
+
+    E, T, S = 65536, 12, 37
+    models, K, flags, pos0, act0, tgt = hetero16(E)
+    pos0 = pos0.copy()
+    tgt = tgt.copy()
+    # envs E-3, E-2, E-1 are exact copies of env 5 (identical envs must stay identical wherever their tile is)
+    for e in (E - 3, E - 2, E - 1):
+        pos0[e] = pos0[5]
+        tgt[e * 16:(e + 1) * 16] = tgt[5 * 16:6 * 16]
+    big = SwarmCore(models, E, aggregate_phy_steps=K, stats=True, **flags)
+    big.reset(pos0, action0=act0)
+    big.step(big.targets_per_vehicle(tgt), T)
+    small = SwarmCore(models, S, aggregate_phy_steps=K, **flags)
+    small.reset(pos0[:S], action0=act0[:S])
+    small.step(small.targets_per_vehicle(tgt[:S * 16]), T)
+    torch.cuda.synchronize()
+    vb, vs = big.views(), small.views()
+    for k in ("pos", "quat", "vel", "omega_body", "last_vel", "last_rates", "cmd0123", "cmd45"):
+        b = vb[k].cpu().numpy()
+        np.testing.assert_array_equal(b[:S * 16], vs[k].cpu().numpy(), err_msg=k)  # batch-size / tile independence
+        for e in (E - 3, E - 2, E - 1):
+            np.testing.assert_array_equal(b[e * 16:(e + 1) * 16], b[5 * 16:6 * 16], err_msg=k)  # identical envs
+    st = big.stats()
+    assert st["non_finite"] == 0 and st["control_evals"] == E * 16 * T and st["wls_non_converged"] == 0
+    assert big.step_counter == T * K
+    # the quads sag during the start-up transient, nobody reaches the ground in 0.4 s
+    assert 1.0 < st["min_altitude"] < 2.1
+    big.close()
+    small.close()
+
+
+@pytest.mark.parametrize("name,E", [("traj_quad", 4096), ("hexa_circle", 65536)])
+def test_full_size_single_type_properties(name, E):
+    """configs[1] (4096 envs, trajectory table) and configs[2] (65,536 envs, hexa circle + ground + drag)."""
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.workloads import single_type
+
+    T, S = 50, 21
+    models, K, flags, pos0, act0, tab, wp0 = single_type(name, E)
+    big = SwarmCore(models, E, aggregate_phy_steps=K, stats=True, **flags)
+    big.reset(pos0, action0=act0, wp0=wp0)
+    big.step(big.targets_table(tab), T)
+    small = SwarmCore(models, S, aggregate_phy_steps=K, **flags)
+    small.reset(pos0[:S], action0=act0[:S], wp0=wp0[:S])
+    small.step(small.targets_table(tab), T)
+    torch.cuda.synchronize()
+    vb, vs = big.views(), small.views()
+    for k in ("pos", "quat", "vel", "omega_body", "cmd0123", "cmd45"):
+        np.testing.assert_array_equal(vb[k].cpu().numpy()[:S], vs[k].cpu().numpy(), err_msg=k)
+    # waypoint counters: wp + 1 if wp < NUM_WP - 1 else 0, T times (fly_INDI.py:242-245) - closed form, bit-exact
+    np.testing.assert_array_equal(vb["wp_counter"].cpu().numpy(), (wp0.astype(np.int64) + T) % tab.shape[0])
+    st = big.stats()
+    assert st["non_finite"] == 0 and st["control_evals"] == E * T and big.step_counter == T * K
+    big.close()
+    small.close()

@@ -40,12 +40,13 @@ class ds_config(C.Structure):
         ("goal_radius", C.c_float), ("done_floor_enable", C.c_int32), ("z_min", C.c_float),
         ("max_steps", C.c_int32), ("env_offset", C.c_int32),
         ("motor_tau", C.c_float), ("acc_filter_hz", C.c_float), ("reward_mode", C.c_int32),
+        ("noise_force_sigma", C.c_float), ("noise_torque_sigma", C.c_float), ("noise_seed", C.c_uint64),
     ]
 
 
 class ds_type_params(C.Structure):
     _fields_ = [
-        ("n_u", C.c_int32), ("n_v", C.c_int32), ("law", C.c_int32), ("reserved", C.c_int32),
+        ("n_u", C.c_int32), ("n_v", C.c_int32), ("law", C.c_int32), ("rotor_model", C.c_int32),
         ("mass", C.c_double), ("J", C.c_double * 9), ("r_com", C.c_double * 3), ("kf", C.c_double), ("km", C.c_double),
         ("rotor_pos", (C.c_double * 3) * _R), ("rotor_axis", (C.c_double * 3) * _R),
         ("torque_axis", (C.c_double * 3) * _R), ("rotor_spin", C.c_double * _R),

@@ -33,6 +33,7 @@ def type_params(vt: VehicleType, composite: bool) -> L.ds_type_params:
     p = L.ds_type_params()
     n_u, n_v = vt.INDI_ACTUATOR_NR, vt.INDI_OUTPUT_NR
     p.n_u, p.n_v, p.law = n_u, n_v, vt.law
+    p.rotor_model = 1 if "morphing_hexa" in vt.TYPE else 0  # which live force model flies it (BaseAviary.py:935-944)
     if composite:
         mass, J, rc = vt.M_TOTAL, np.asarray(vt.J_TOTAL, float), np.asarray(vt.COM, float)
     else:
@@ -84,7 +85,8 @@ class SwarmCore:
                  freq: float = 240.0, aggregate_phy_steps: int = 1, neighbourhood_radius: float = math.inf,
                  gravity: float = 9.8, goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0,
                  device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None, dw_ordered_pairs: bool = False,
-                 motor_tau: float = 0.0, acc_filter_hz: float = 0.0, reward_mode: int = 0):
+                 motor_tau: float = 0.0, acc_filter_hz: float = 0.0, reward_mode: int = 0,
+                 noise_force_sigma: float = 0.0, noise_torque_sigma: float = 0.0, noise_seed: int = 0):
         lib = L.lib()
         self.vehicle_types: List[VehicleType] = [m if isinstance(m, VehicleType) else load_vehicle(m, assets_dir)
                                                  for m in slot_models]
@@ -115,6 +117,8 @@ class SwarmCore:
         cfg.max_steps, cfg.env_offset = int(max_steps), int(env_offset)
         # extensions beyond the reference (north_star): first-order motor lag, low-passed angular acceleration, tracking reward
         cfg.motor_tau, cfg.acc_filter_hz, cfg.reward_mode = float(motor_tau), float(acc_filter_hz), int(reward_mode)
+        cfg.noise_force_sigma, cfg.noise_torque_sigma = float(noise_force_sigma), float(noise_torque_sigma)
+        cfg.noise_seed = int(noise_seed) & 0xFFFFFFFFFFFFFFFF
         self._h = C.c_void_p()
         L.check(lib.ds_create(C.byref(cfg), C.byref(self._h)))
         # distinct types, in order of first appearance

@@ -105,7 +105,8 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   if (cfg->integrator != DS_INTEG_QUAT && cfg->integrator != DS_INTEG_RPY) return DS_ERR_INVALID;
   if ((int64_t)cfg->n_envs * cfg->drones_per_env > (int64_t)1 << 30) return DS_ERR_UNSUPPORTED;
   if (cfg->motor_tau < 0.f || cfg->acc_filter_hz < 0.f || cfg->reward_mode < 0 || cfg->reward_mode > 1) return DS_ERR_INVALID;
-  const bool want_ext = cfg->motor_tau > 0.f || cfg->acc_filter_hz > 0.f;
+  if (cfg->noise_force_sigma < 0.f || cfg->noise_torque_sigma < 0.f) return DS_ERR_INVALID;
+  const bool want_ext = cfg->motor_tau > 0.f || cfg->acc_filter_hz > 0.f || cfg->noise_force_sigma > 0.f || cfg->noise_torque_sigma > 0.f;
   if (want_ext && cfg->integrator == DS_INTEG_RPY) return DS_ERR_UNSUPPORTED;
   ds_handle* h = new (std::nothrow) ds_handle();
   if (!h) return DS_ERR_INVALID;
@@ -186,6 +187,8 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     const ds_type_params& p = types[t];
     if (p.n_u < 1 || p.n_u > DS_MAX_ROTORS || p.n_v < 1 || p.n_v > DS_MAX_ROTORS) return DS_ERR_INVALID;
     if (p.law != DS_LAW_QUAD && p.law != DS_LAW_6DOF) return DS_ERR_INVALID;
+    if (p.rotor_model != 0 && p.rotor_model != 1) return DS_ERR_INVALID;
+    if (!(p.km > 0.0)) return DS_ERR_INVALID;
     if (p.law == DS_LAW_6DOF && (p.n_u != 6 || p.n_v != 6)) return DS_ERR_UNSUPPORTED;
     if (p.law == DS_LAW_QUAD && p.n_v != 4) return DS_ERR_UNSUPPORTED;
     if (!(p.mass > 0.0) || !(p.kf > 0.0)) return DS_ERR_INVALID;
@@ -215,6 +218,9 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     d.n_u = p.n_u;
     d.law = p.law;
     d.speed_limit = (float)(p.max_speed_kmh * (1000.0 / 3600.0));
+    d.rotor_model = p.rotor_model;
+    d.kf_over_km = (float)(p.kf / p.km);
+    double lat[3] = {0.0, 0.0, 0.0};
     double rpm0 = 0.0;
     for (int i = 0; i < p.n_u; ++i) {
       DsRotorDev& r = d.rotor[i];
@@ -230,9 +236,11 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
       r.scale = (float)p.pwm2rpm_scale[i]; r.cnst = (float)p.pwm2rpm_const[i];
       r.pmin = (float)p.min_pwm[i]; r.pmax = (float)p.max_pwm[i];
       rpm0 += p.pwm2rpm_const[i];
+      for (int k = 0; k < 3; ++k) lat[k] += rel[k];
       for (int j = 0; j < p.n_v; ++j) d.alloc[i * 6 + j] = (float)p.alloc[i][j];
     }
     d.rpm0_sum = (float)rpm0;
+    for (int k = 0; k < 3; ++k) d.lat[k] = (float)lat[k];
     if (p.n_u > 4) h->nu6 = true;
     if (t == 0) { h->any_6dof = false; h->rc_kind = 0; }
     if (d.has_rc == 1) h->rc_kind = 1;
@@ -343,6 +351,10 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.ext = h->ext ? 1 : 0;
   a.motor_a = h->cfg.motor_tau > 0.f ? (float)(1.0 - exp(-(1.0 / (double)h->cfg.sim_freq) / (double)h->cfg.motor_tau)) : 2.0f;
   a.acc_b = 2.0f;  // set with the control time step (set_filter)
+  a.noise_f = h->cfg.noise_force_sigma; a.noise_m = h->cfg.noise_torque_sigma;
+  a.seed_lo = (uint32_t)(h->cfg.noise_seed & 0xffffffffu); a.seed_hi = (uint32_t)(h->cfg.noise_seed >> 32);
+  a.veh0 = (uint32_t)((int64_t)h->cfg.env_offset * h->cfg.drones_per_env);
+  a.step0 = (uint32_t)h->step_counter;
   a.flags = h->cfg.flags & 0xFu;
   a.dt = 1.0f / h->cfg.sim_freq;
   a.gravity = h->cfg.gravity;
@@ -410,6 +422,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   cudaStream_t st = (cudaStream_t)stream;
   for (int i = 0; i < n_control_steps; ++i) {
     a.use_act = (h->first_action_pending && order == 0) ? 1 : 0;
+    a.step0 = (uint32_t)h->step_counter;  // substep index of k = 0 (noise stream counter)
     a.store_act = 0;
     time_flags(h, a);
     launch_step<0>(h, a, st);

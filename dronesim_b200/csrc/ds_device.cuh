@@ -46,7 +46,10 @@ struct __align__(16) DsTypeDev {
   float rpm0_sum;            // sum_i PWM2RPM_CONST_i  (rpm of the all-zero action, BaseAviary.py:659-662)
   int has_rc;                // centre of mass vs base-frame origin (QUAT integrator): 0 same point, 1 general offset, 2 offset along body z only
   float speed_limit;         // MAX_SPEED_KMH * 1000 / 3600 (VelocityAviary.py:92-94)
-  float pad_[23];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
+  float lat[3];              // sum_i (r_i - rc): arm of the quad model's lateral noise force (BaseAviary.py:1528-1536)
+  int rotor_model;           // 0 quad (_quad_copter_physics), 1 morphing hexa (_morphing_hexa_physics)
+  float kf_over_km;          // turns the stored reaction-torque column (m - g) = spin km/kf t into spin t
+  float pad_[18];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
 };
 static_assert(sizeof(DsTypeDev) % 16 == 0, "DsTypeDev must be float4-copyable");
 static_assert((sizeof(DsTypeDev) / 4) % 32 == 8, "DsTypeDev bank stride");
@@ -97,6 +100,11 @@ struct DsArgs {
   int ext;          // 1: the EXT kernel variant runs (motor model and / or angular-acceleration filter on)
   float motor_a;    // 1 - exp(-dt / tau_motor); >= 1: static map (BaseAviary.py:1487-1490)
   float acc_b;      // 1 - exp(-2 pi f_c ctrl_dt); >= 1: raw finite difference (INDIControl.py:432-439)
+  // rotor noise (BaseAviary.py:1429-1432, 1518-1525), EXT variant only; sigma = 0: off
+  float noise_f, noise_m;
+  uint32_t seed_lo, seed_hi;
+  uint32_t veh0;    // global id of this shard's vehicle 0 (env_offset * D): the noise stream does not depend on sharding
+  uint32_t step0;   // step_counter at launch: substep index of k = 0
   // targets
   int tmode, num_wp, advance_wp;
   const float4* t_pos;
@@ -180,3 +188,34 @@ __device__ __forceinline__ float4 ds_quat_from_euler(float r, float p, float y) 
 }
 
 __device__ __forceinline__ float ds_clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------
+// counter-based noise: Philox-4x32-10 keyed by the seed, counter = (vehicle, substep, draw, 0); Box-Muller on 24-bit
+// uniforms.  oracle/noise.py is the FP64 twin (same integers, same uniforms).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ds_philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ void ds_box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincosf(6.28318530717958647692f * u2, &sn, &cs);
+  n0 = r * cs; n1 = r * sn;
+}
+// 12 standard normals of (vehicle, substep): draws 0..2
+__device__ __forceinline__ void ds_normals12(uint32_t veh, uint32_t substep, uint32_t k0, uint32_t k1, float n[12]) {
+#pragma unroll
+  for (uint32_t j = 0; j < 3; ++j) {
+    const uint4 x = ds_philox4x32(make_uint4(veh, substep, j, 0u), k0, k1);
+    ds_box_muller(x.x, x.y, n[4 * j], n[4 * j + 1]);
+    ds_box_muller(x.z, x.w, n[4 * j + 2], n[4 * j + 3]);
+  }
+}

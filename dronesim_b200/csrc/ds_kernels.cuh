@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
       rpm[0] = R0.x; rpm[1] = R0.y; rpm[2] = R0.z; rpm[3] = R0.w;
       if (NU6) { const float2 R1 = a.s_r1[vv]; rpm[4] = R1.x; rpm[5] = R1.y; }
     }
-    ds_physics<INTEG, DW, NU6, WARPSYNC, FX, EXT>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum, rpm);
+    ds_physics<INTEG, DW, NU6, WARPSYNC, FX, EXT>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum, rpm, a.veh0 + (uint32_t)vv);
     if (MODE == 0 && a.order == 0) control();
     if (MODE == 1) done_bits = __float_as_uint(sg[SG_LV * T + ld].w);
 

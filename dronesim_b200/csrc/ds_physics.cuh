@@ -161,7 +161,8 @@ __device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict_
 // every substep moves them towards the commanded speed and rebuilds the rotor wrench, so nothing is hoisted.
 template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX, bool EXT>
 __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_row0, int my_row, float4* sh_pos,
-                                           const float* act, PhysState& s, float& prev_rpm_sum, float* rpm_state) {
+                                           const float* act, PhysState& s, float& prev_rpm_sum, float* rpm_state,
+                                           uint32_t veh_id) {
   constexpr int NU = NU6 ? 6 : 4;
   const float dt = a.dt;
   const bool gnd = (FX >= 0) ? ((FX & 1) != 0) : ((a.flags & 1u) != 0);
@@ -177,8 +178,22 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   // the substeps), or once per substep when the motor model moves the rotor speeds
   float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
   float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
-  auto rotor_wrench = [&]() {
+  auto rotor_wrench = [&](int k) {
     rpm_sum = 0.f; F0x = 0.f; F0y = 0.f; F0z = 0.f; t0x = 0.f; t0y = 0.f; t0z = 0.f;
+    // rotor noise (EXT; BaseAviary.py:1429-1432, 1518-1525): per substep N(0, sigma_f) on every thrust, N(0, sigma_m) on
+    // every reaction torque; the quad model also puts (f_noise[0], f_noise[1]) on every rotor link laterally and
+    // (m_noise[0], m_noise[1]) on the base (:1528-1543).  Ground effect keeps the noise-free thrust (:1680-1685).
+    const bool noisy = EXT && (a.noise_f > 0.f || a.noise_m > 0.f);
+    float nz[12];
+    if (noisy) {
+      ds_normals12(veh_id, a.step0 + (uint32_t)k, a.seed_lo, a.seed_hi, nz);
+      if (tp.rotor_model == 0) {
+        const float l0 = a.noise_f * nz[0], l1 = a.noise_f * nz[1], nn = (float)tp.n_u;
+        F0x = nn * l0; F0y = nn * l1;
+        t0x = -tp.lat[2] * l1 + a.noise_m * nz[6]; t0y = tp.lat[2] * l0 + a.noise_m * nz[7];
+        t0z = tp.lat[0] * l1 - tp.lat[1] * l0;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NU; ++i) {  // rotors beyond n_u have scale = const = 0 -> T = 0
       const DsRotorDev& r = tp.rotor[i];
@@ -192,9 +207,14 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
       Tg[i] = T * tp.gnd_k;
       F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
       t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
+      if (noisy && i < tp.n_u) {
+        const float nf = a.noise_f * nz[i], nm = a.noise_m * nz[6 + i] * tp.kf_over_km;
+        F0x = fmaf(nf, r.ax, F0x); F0y = fmaf(nf, r.ay, F0y); F0z = fmaf(nf, r.az, F0z);
+        t0x += nf * r.gx + nm * (r.mx - r.gx); t0y += nf * r.gy + nm * (r.my - r.gy); t0z += nf * r.gz + nm * (r.mz - r.gz);
+      }
     }
   };
-  if (!EXT) rotor_wrench();
+  if (!EXT) rotor_wrench(0);
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
 
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
@@ -235,7 +255,7 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   for (int k = 0; k < a.K; ++k) {
     if (EXT) {  // drag sees the rotor speeds before this substep's motor update
       if (k > 0) prev_rpm_sum = rpm_sum;
-      rotor_wrench();
+      rotor_wrench(k);
     }
     // ---- downwash first (BaseAviary.py:1747-1763): it needs the base-frame origin only, so the rotation matrix
     // does not have to stay live (or be rematerialised) across the unrolled pair loop

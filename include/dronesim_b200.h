@@ -91,6 +91,14 @@ typedef struct ds_config {
   float acc_filter_hz;     /* Hz: first-order low-pass on the INDI angular-acceleration estimate; 0 = the raw finite
                               difference (the reference's filter is a commented placeholder, INDIControl.py:432-439) */
   int32_t reward_mode;     /* 0: constant -1 (CtrlAviary.py:267-278); 1: minus the env's mean |pos_e| of the last control step */
+  /* Rotor noise of the live force models (BaseAviary.py:1429-1432, 1518-1525: N(0, 0.01) on every rotor thrust,
+   * N(0, 0.001) on every reaction torque, plus the quad model's lateral / base terms :1528-1543), per substep.  The
+   * reference draws it from the unseeded global numpy generator; here it is a counter-based stream (Philox-4x32-10,
+   * Box-Muller) keyed by `noise_seed` and indexed by (global vehicle id, substep), so a run is reproducible and does
+   * not depend on how the envs are sharded.  sigma = 0: off (all parity runs). */
+  float noise_force_sigma;
+  float noise_torque_sigma;
+  uint64_t noise_seed;
 } ds_config;
 
 /* Per-type constants.  Field sources: BaseAviary._parseURDFParameters (BaseAviary.py:2041-2140),
@@ -99,7 +107,7 @@ typedef struct ds_type_params {
   int32_t n_u;   /* INDI_ACTUATOR_NR */
   int32_t n_v;   /* INDI_OUTPUT_NR */
   int32_t law;   /* DS_LAW_* */
-  int32_t reserved;
+  int32_t rotor_model; /* 0: quad, forces on links 0..n_u-1 + one base torque (BaseAviary.py:1477-1543); 1: morphing hexa (:1389-1457) */
   double mass;          /* M (literal) or whole-tree mass */
   double J[9];          /* row-major inertia about the centre of mass, body axes */
   double r_com[3];      /* centre of mass in the base frame */

@@ -103,15 +103,28 @@ def quat_exp(w, dt):
     return np.array([th[0] * k, th[1] * k, th[2] * k, math.cos(half)])
 
 
-def body_wrench(pp, cmd, cmd_prev_rpm_sum, pos, quat, rpy, vel, others_pos, gnd, drag, dw, rpm=None):
+def body_wrench(pp, cmd, cmd_prev_rpm_sum, pos, quat, rpy, vel, others_pos, gnd, drag, dw, rpm=None, noise=None):
     """Body-frame force and torque about the (composite) centre of mass for one substep.
-    ``rpm``: actual rotor speeds when the first-order motor model (extension, R9) is on; default = the static map."""
+    ``rpm``: actual rotor speeds when the first-order motor model (extension, R9) is on; default = the static map.
+    ``noise``: (f_noise[n_u], m_noise[n_u]) of this substep (:1429-1432 / :1518-1525) or None (noise off)."""
     R = p.rotmat(quat)
     rpm = rpm_of_cmd(pp, cmd) if rpm is None else np.asarray(rpm, float)
     T = pp.kf * rpm**2  # :1515 / :1402
     Q = pp.km * rpm**2  # :1516 / :1403
     F = np.zeros(3)
     tau = np.zeros(3)
+    if noise is not None:
+        f_noise, m_noise = noise
+        T = T + f_noise  # forces += f_noise (:1433 / :1524)
+        Q = Q + m_noise  # torques += m_noise (:1434 / :1525)
+        if "morphing_hexa" not in pp.vt.TYPE:
+            # quad model: every rotor link also gets (f_noise[0], f_noise[1]) laterally (:1528-1536) and the base
+            # gets (m_noise[0], m_noise[1]) (:1537-1543); the quads' link frames are the body frame
+            lat = np.array([f_noise[0], f_noise[1], 0.0])
+            for i in range(pp.n_u):
+                F += lat
+                tau += np.cross(pp.rotor_pos[i] - pp.r_com, lat)
+            tau += np.array([m_noise[0], m_noise[1], 0.0])
     for i in range(pp.n_u):
         f = T[i] * pp.rotor_axis[i]
         F += f

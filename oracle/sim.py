@@ -30,7 +30,7 @@ DONE_TIME = 4  # step_counter >= max_steps     (beyond the reference; off by def
 class OracleSwarm:
     def __init__(self, slot_types, n_envs, integrator="quat", composite=True, gnd=False, drag=False,
                  dw=False, freq=240, aggregate_phy_steps=1, neighbourhood_radius=np.inf, motor_tau=0.0,
-                 acc_filter_hz=0.0):
+                 acc_filter_hz=0.0, noise_force_sigma=0.0, noise_torque_sigma=0.0, noise_seed=0, env_offset=0):
         """``slot_types``: list of VehicleType, one per drone slot of an env (the reference's
         ``drone_model`` list, BaseAviary.py:131,219); every env has the same slot->type map."""
         self.E, self.D = int(n_envs), len(slot_types)
@@ -53,6 +53,9 @@ class OracleSwarm:
             for row in self.ctrl:
                 for c in row:
                     c.acc_b = b
+        # rotor noise: the reference's N(0, 0.01) / N(0, 0.001) draws, from a counter-based source (oracle/noise.py)
+        self.noise_f, self.noise_m = float(noise_force_sigma), float(noise_torque_sigma)
+        self.noise_seed, self.env_offset = int(noise_seed), int(env_offset)
         self.goal = None
         self.goal_radius = 0.3
         self.z_min = None
@@ -112,7 +115,7 @@ class OracleSwarm:
             for d in range(self.D):
                 n, pp = self.n_u[d], self.pp[d]
                 clipped[d, :n] = np.clip(action[e, d, :n], pp.min_pwm, pp.max_pwm)  # CtrlAviary.py:258-263
-            for _ in range(self.K):
+            for _k in range(self.K):
                 snap_pos = self.pos[e].copy()  # the state cache all drones read (BaseAviary.py:513-520)
                 new = []
                 for d in range(self.D):
@@ -124,8 +127,14 @@ class OracleSwarm:
                         prev_sum = float(np.sum(self.rpm[e, d, :n]))
                         self.rpm[e, d, :n] += self.motor_a * (od.rpm_of_cmd(pp, clipped[d, :n]) - self.rpm[e, d, :n])
                         rpm = self.rpm[e, d, :n]
+                    noise = None
+                    if self.noise_f > 0 or self.noise_m > 0:
+                        from . import noise as on
+                        nz = on.normals12((self.env_offset + e) * self.D + d, self.step_counter + _k, self.noise_seed)
+                        noise = (self.noise_f * nz[0:n], self.noise_m * nz[6:6 + n])
                     F, tau, R = od.body_wrench(pp, clipped[d, :n], prev_sum, snap_pos[d], self.quat[e, d],
-                                               self.rpy[e, d], self.vel[e, d], others, self.gnd, self.drag, self.dw, rpm=rpm)
+                                               self.rpy[e, d], self.vel[e, d], others, self.gnd, self.drag, self.dw, rpm=rpm,
+                                               noise=noise)
                     if self.integrator == "rpy":
                         new.append(od.substep_rpy(pp, dt, snap_pos[d], self.quat[e, d], self.rpy[e, d],
                                                   self.vel[e, d], self.rates[e, d], F, tau, R))

@@ -614,3 +614,56 @@ def test_full_size_single_type_properties(name, E):
     assert st["non_finite"] == 0 and st["control_evals"] == E * T and big.step_counter == T * K
     big.close()
     small.close()
+
+
+# ------------------------------------------------------------------------------------------
+# rotor noise (BaseAviary.py:1429-1432, 1518-1543) from the counter-based source: same stream in the oracle, so the
+# noisy closed loop is compared trajectory-for-trajectory; reproducible; independent of the sharding
+# ------------------------------------------------------------------------------------------
+def test_rotor_noise_stream_parity_and_sharding():
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    models = ["robobee", "hexa_6DOF", "tello", "hexa_6DOF_simple"]
+    D, E, K, SEED = 4, 4, 5, 0x1234ABCD5678
+    kw = dict(noise_force_sigma=0.01, noise_torque_sigma=0.001, noise_seed=SEED)  # the reference's sigmas
+    core, orc = make_pair(models, E, "quat", K=K, gnd=True, drag=True, **kw)
+    for o in (orc,):
+        o.noise_f, o.noise_m, o.noise_seed = 0.01, 0.001, SEED
+    pos0 = np.zeros((E, D, 3))
+    for s_ in range(D):
+        pos0[:, s_] = [1.5 * s_, 0.0, 2.0]
+    act0 = np.zeros((E, D, 6))
+    for s_, m in enumerate(models):
+        act0[:, s_, : (6 if "hexa" in m else 4)] = 0.45
+    core.reset(pos0, action0=act0)
+    orc.reset(pos0)
+    tgt = np.concatenate([pos0.reshape(-1, 3), np.zeros((E * D, 1))], axis=1)
+    act = act0.copy()
+    for step in range(24):  # 0.5 s
+        core.step(core.targets_per_vehicle(tgt), 1)
+        orc.physics_step(act)
+        act = orc.control_step(pos0)
+    _compare_state(core, orc, pos_tol=2e-4, att_tol=3e-4, vel_tol=5e-3, what="noisy closed loop")
+    noisy = core_state(core)["pos"].copy()
+    core.close()
+    # identical envs diverge (each vehicle has its own stream) ...
+    assert np.abs(noisy.reshape(E, D, 3)[0] - noisy.reshape(E, D, 3)[1]).max() > 1e-6
+    # ... the same seed reproduces the run bit-exactly, another seed does not ...
+    runs = []
+    for seed in (SEED, SEED, SEED + 1):
+        c = SwarmCore(models, E, aggregate_phy_steps=K, ground=True, drag=True, noise_force_sigma=0.01, noise_torque_sigma=0.001,
+                      noise_seed=seed)
+        c.reset(pos0, action0=act0)
+        c.step(c.targets_per_vehicle(tgt), 24)
+        runs.append(core_state(c)["pos"].copy())
+        c.close()
+    np.testing.assert_array_equal(runs[0], noisy)
+    np.testing.assert_array_equal(runs[0], runs[1])
+    assert np.abs(runs[0] - runs[2]).max() > 1e-6
+    # ... and a shard holding envs 2..3 (env_offset = 2) reproduces those envs of the full run
+    c = SwarmCore(models, 2, aggregate_phy_steps=K, ground=True, drag=True, env_offset=2, **kw)
+    c.reset(pos0[2:], action0=act0[2:])
+    c.step(c.targets_per_vehicle(tgt[2 * D:]), 24)
+    np.testing.assert_array_equal(core_state(c)["pos"], noisy[2 * D:])
+    c.close()

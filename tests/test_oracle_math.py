@@ -100,3 +100,17 @@ def test_integer_bookkeeping():
     np.testing.assert_array_equal(sw.adjacency_bits(), [[0b011, 0b111, 0b110], [0b001, 0b010, 0b100]])  # strict <
     sw.physics_step(np.zeros((2, 3, 6)))
     assert sw.step_counter == 5  # BaseAviary.py:554
+
+
+def test_philox_known_answers_and_normals():
+    """The noise source (extension: the reference uses the unseeded global numpy generator) is Philox-4x32-10; the
+    three known-answer vectors are the ones published with Random123 (kat_vectors, philox4x32 10 rounds)."""
+    from oracle import noise as on
+
+    assert on.philox4x32((0, 0, 0, 0), 0, 0) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert on.philox4x32((0xFFFFFFFF,) * 4, 0xFFFFFFFF, 0xFFFFFFFF) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert on.philox4x32((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), 0xA4093822, 0x299F31D0) == (
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+    z = np.array([on.normals12(v, s_, 1234) for v in range(200) for s_ in range(10)]).reshape(-1)
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03 and abs((z**3).mean()) < 0.1
+    assert not np.array_equal(on.normals12(1, 2, 3), on.normals12(2, 1, 3))

@@ -57,7 +57,7 @@ class ds_type_params(C.Structure):
         ("kp_pos", C.c_double), ("kd_pos", C.c_double), ("att_gain", C.c_double * 3), ("rate_gain", C.c_double * 3),
         ("G1", (C.c_double * _R) * _R), ("alloc", (C.c_double * _R) * _R),
         ("wls_wv", C.c_double * _R), ("wls_gamma", C.c_double), ("init_cmd", C.c_double), ("init_thrust", C.c_double),
-        ("max_speed_kmh", C.c_double),
+        ("max_speed_kmh", C.c_double), ("adv_coeff", C.c_double * 14), ("adv_radius", C.c_double),
     ]
 
 

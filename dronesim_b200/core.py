@@ -34,6 +34,14 @@ def type_params(vt: VehicleType, composite: bool) -> L.ds_type_params:
     n_u, n_v = vt.INDI_ACTUATOR_NR, vt.INDI_OUTPUT_NR
     p.n_u, p.n_v, p.law = n_u, n_v, vt.law
     p.rotor_model = 1 if "morphing_hexa" in vt.TYPE else 0  # which live force model flies it (BaseAviary.py:935-944)
+    if "advanced" in vt.TYPE and p.rotor_model == 0:  # BaseAviary.py:1493
+        from .vehicles import load_propeller
+
+        prop = load_propeller()
+        p.rotor_model = 2
+        for i in range(14):
+            p.adv_coeff[i] = prop["coeff"][i]
+        p.adv_radius = prop["radius"]
     if composite:
         mass, J, rc = vt.M_TOTAL, np.asarray(vt.J_TOTAL, float), np.asarray(vt.COM, float)
     else:

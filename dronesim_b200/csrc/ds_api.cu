@@ -183,11 +183,13 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
   memset(dev.data(), 0, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
   memset(wls.data(), 0, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
   h->nu6 = false;
+  bool need_ext = false;  // the advanced propeller model runs in the EXT kernel variant
   for (int t = 0; t < n_types; ++t) {
     const ds_type_params& p = types[t];
     if (p.n_u < 1 || p.n_u > DS_MAX_ROTORS || p.n_v < 1 || p.n_v > DS_MAX_ROTORS) return DS_ERR_INVALID;
     if (p.law != DS_LAW_QUAD && p.law != DS_LAW_6DOF) return DS_ERR_INVALID;
-    if (p.rotor_model != 0 && p.rotor_model != 1) return DS_ERR_INVALID;
+    if (p.rotor_model < 0 || p.rotor_model > 2) return DS_ERR_INVALID;
+    if (p.rotor_model == 2 && (h->cfg.integrator == DS_INTEG_RPY || p.n_u != 4 || !(p.adv_radius > 0.0))) return DS_ERR_UNSUPPORTED;
     if (!(p.km > 0.0)) return DS_ERR_INVALID;
     if (p.law == DS_LAW_6DOF && (p.n_u != 6 || p.n_v != 6)) return DS_ERR_UNSUPPORTED;
     if (p.law == DS_LAW_QUAD && p.n_v != 4) return DS_ERR_UNSUPPORTED;
@@ -220,6 +222,9 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     d.speed_limit = (float)(p.max_speed_kmh * (1000.0 / 3600.0));
     d.rotor_model = p.rotor_model;
     d.kf_over_km = (float)(p.kf / p.km);
+    for (int i = 0; i < 14; ++i) d.adv[i] = (float)p.adv_coeff[i];
+    d.adv[14] = (float)p.adv_radius;
+    if (p.rotor_model == 2) need_ext = true;
     double lat[3] = {0.0, 0.0, 0.0};
     double rpm0 = 0.0;
     for (int i = 0; i < p.n_u; ++i) {
@@ -263,6 +268,12 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     h->slot_type[s] = slot_type[s];
   }
   h->n_types = n_types;
+  if (need_ext && !h->ext) {
+    const size_t np = (size_t)h->n_pad;
+    CK(cudaMalloc((void**)&h->s_r0, np * 16)); CK(cudaMalloc((void**)&h->s_r1, np * 8)); CK(cudaMalloc((void**)&h->s_af, np * 16));
+    CK(cudaMemset(h->s_r0, 0, np * 16)); CK(cudaMemset(h->s_r1, 0, np * 8)); CK(cudaMemset(h->s_af, 0, np * 16));
+    h->ext = true;
+  }
   CK(cudaMemcpy(h->d_types, dev.data(), sizeof(DsTypeDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_wls, wls.data(), sizeof(DsWlsDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_slot_type, h->slot_type, h->cfg.drones_per_env, cudaMemcpyHostToDevice));

@@ -47,9 +47,10 @@ struct __align__(16) DsTypeDev {
   int has_rc;                // centre of mass vs base-frame origin (QUAT integrator): 0 same point, 1 general offset, 2 offset along body z only
   float speed_limit;         // MAX_SPEED_KMH * 1000 / 3600 (VelocityAviary.py:92-94)
   float lat[3];              // sum_i (r_i - rc): arm of the quad model's lateral noise force (BaseAviary.py:1528-1536)
-  int rotor_model;           // 0 quad (_quad_copter_physics), 1 morphing hexa (_morphing_hexa_physics)
+  int rotor_model;           // 0 quad (_quad_copter_physics), 1 morphing hexa (_morphing_hexa_physics), 2 quad "advanced" (:1493-1512)
   float kf_over_km;          // turns the stored reaction-torque column (m - g) = spin km/kf t into spin t
-  float pad_[18];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
+  float adv[15];             // rotor_model 2: the 14 oblique-flow coefficients (Data_section5_ObliqueFlow) + propeller radius [m]
+  float pad_[3];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
 };
 static_assert(sizeof(DsTypeDev) % 16 == 0, "DsTypeDev must be float4-copyable");
 static_assert((sizeof(DsTypeDev) / 4) % 32 == 8, "DsTypeDev bank stride");

@@ -174,47 +174,6 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   const bool has_rc = rc_kind != 0;
   const bool rc_gen = rc_kind == 1;
 
-  // ---- rotor thrusts and the rotor part of the body wrench: once per control step (the command is constant across
-  // the substeps), or once per substep when the motor model moves the rotor speeds
-  float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
-  float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
-  auto rotor_wrench = [&](int k) {
-    rpm_sum = 0.f; F0x = 0.f; F0y = 0.f; F0z = 0.f; t0x = 0.f; t0y = 0.f; t0z = 0.f;
-    // rotor noise (EXT; BaseAviary.py:1429-1432, 1518-1525): per substep N(0, sigma_f) on every thrust, N(0, sigma_m) on
-    // every reaction torque; the quad model also puts (f_noise[0], f_noise[1]) on every rotor link laterally and
-    // (m_noise[0], m_noise[1]) on the base (:1528-1543).  Ground effect keeps the noise-free thrust (:1680-1685).
-    const bool noisy = EXT && (a.noise_f > 0.f || a.noise_m > 0.f);
-    float nz[12];
-    if (noisy) {
-      ds_normals12(veh_id, a.step0 + (uint32_t)k, a.seed_lo, a.seed_hi, nz);
-      if (tp.rotor_model == 0) {
-        const float l0 = a.noise_f * nz[0], l1 = a.noise_f * nz[1], nn = (float)tp.n_u;
-        F0x = nn * l0; F0y = nn * l1;
-        t0x = -tp.lat[2] * l1 + a.noise_m * nz[6]; t0y = tp.lat[2] * l0 + a.noise_m * nz[7];
-        t0z = tp.lat[0] * l1 - tp.lat[1] * l0;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {  // rotors beyond n_u have scale = const = 0 -> T = 0
-      const DsRotorDev& r = tp.rotor[i];
-      float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
-      if (EXT) {
-        rpm = (a.motor_a >= 1.f) ? rpm : fmaf(a.motor_a, rpm - rpm_state[i], rpm_state[i]);
-        rpm_state[i] = rpm;
-      }
-      rpm_sum += rpm;
-      float T = tp.kf * rpm * rpm;                // :1515
-      Tg[i] = T * tp.gnd_k;
-      F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
-      t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
-      if (noisy && i < tp.n_u) {
-        const float nf = a.noise_f * nz[i], nm = a.noise_m * nz[6 + i] * tp.kf_over_km;
-        F0x = fmaf(nf, r.ax, F0x); F0y = fmaf(nf, r.ay, F0y); F0z = fmaf(nf, r.az, F0z);
-        t0x += nf * r.gx + nm * (r.mx - r.gx); t0y += nf * r.gy + nm * (r.my - r.gy); t0z += nf * r.gz + nm * (r.mz - r.gz);
-      }
-    }
-  };
-  if (!EXT) rotor_wrench(0);
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
 
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
@@ -249,6 +208,84 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
     rot_wxrc(R, ox, oy, oz);
     ux += ox; uy += oy; uz += oz;
   }
+  // ---- rotor thrusts and the rotor part of the body wrench: once per control step (the command is constant across
+  // the substeps), or once per substep when the motor model moves the rotor speeds
+  float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
+  float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
+  auto rotor_wrench = [&](int k) {
+    rpm_sum = 0.f; F0x = 0.f; F0y = 0.f; F0z = 0.f; t0x = 0.f; t0y = 0.f; t0z = 0.f;
+    // rotor noise (EXT; BaseAviary.py:1429-1432, 1518-1525): per substep N(0, sigma_f) on every thrust, N(0, sigma_m) on
+    // every reaction torque; the quad model also puts (f_noise[0], f_noise[1]) on every rotor link laterally and
+    // (m_noise[0], m_noise[1]) on the base (:1528-1543).  Ground effect keeps the noise-free thrust (:1680-1685).
+    const bool noisy = EXT && (a.noise_f > 0.f || a.noise_m > 0.f) && tp.rotor_model != 2;  // no noise on the advanced branch
+    float nz[12];
+    if (noisy) {
+      ds_normals12(veh_id, a.step0 + (uint32_t)k, a.seed_lo, a.seed_hi, nz);
+      if (tp.rotor_model == 0) {
+        const float l0 = a.noise_f * nz[0], l1 = a.noise_f * nz[1], nn = (float)tp.n_u;
+        F0x = nn * l0; F0y = nn * l1;
+        t0x = -tp.lat[2] * l1 + a.noise_m * nz[6]; t0y = tp.lat[2] * l0 + a.noise_m * nz[7];
+        t0z = tp.lat[0] * l1 - tp.lat[1] * l0;
+      }
+    }
+    // "advanced" quad types (EXT; BaseAviary.py:1493-1512 -> _get_prop_FMs :1570-1644 -> utils.py:149-202, 343-416, method 2):
+    // oblique-flow propeller fit instead of KF rpm^2 / KM rpm^2; flow angles from the base velocity rotated by R (sic)
+    const bool adv = EXT && tp.rotor_model == 2;
+    float adv_vs = 0.f, adv_vc = 0.f, adv_cp = 1.f, adv_sp = 0.f;  // V sin(beta), V cos(beta), cos(psi), sin(psi)
+    if (adv) {
+      const Mat3 Ra = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
+      float vx = ux, vy = uy, vz = uz;
+      if (has_rc) { float ox, oy, oz; rot_wxrc(Ra, ox, oy, oz); vx -= ox; vy -= oy; vz -= oz; }
+      const float V = sqrtf(vx * vx + vy * vy + vz * vz);
+      if (!(V > 0.1f)) { vx = 0.1f; vy = 0.f; vz = 0.f; }  // :1585-1589
+      const float bx = Ra.m00 * vx + Ra.m01 * vy + Ra.m02 * vz, by = Ra.m10 * vx + Ra.m11 * vy + Ra.m12 * vz;
+      const float bz = Ra.m20 * vx + Ra.m21 * vy + Ra.m22 * vz;
+      const float cb = ds_clampf(bz * rsqrtf(bx * bx + by * by + bz * bz), -1.f, 1.f);  // cos(beta), beta = arccos (:1600)
+      adv_vc = V * cb; adv_vs = V * sqrtf(fmaxf(1.f - cb * cb, 0.f));
+      if (bx > 0.1f) {  // psi = arctan(by / bx) (:1603-1605): cos > 0
+        const float t = by / bx, ic = rsqrtf(1.f + t * t);
+        adv_cp = ic; adv_sp = t * ic;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {  // rotors beyond n_u have scale = const = 0 -> T = 0
+      const DsRotorDev& r = tp.rotor[i];
+      float rpm = fmaf(r.scale, act[i], r.cnst);  // BaseAviary.py:1487-1490
+      if (EXT) {
+        rpm = (a.motor_a >= 1.f) ? rpm : fmaf(a.motor_a, rpm - rpm_state[i], rpm_state[i]);
+        rpm_state[i] = rpm;
+      }
+      rpm_sum += rpm;
+      float T = tp.kf * rpm * rpm;                // :1515
+      Tg[i] = T * tp.gnd_k;
+      if (adv) {
+        if (i < tp.n_u) {
+          const float* c = tp.adv;  // CstaticFT k1 k2 k3 k4 k5 CstaticMQ k6 k7 k8 k9 k10 k11 k12 | radius
+          const float Rp = c[14];
+          const float om = fmaxf(rpm * (6.28318530717958647692f / 60.0f), 10.0f);  // utils.py:176
+          const float inv = 1.0f / (om * Rp);
+          const float mu = adv_vs * inv, lc = adv_vc * inv;                          // utils.py:383-384
+          const float cft = c[0] + c[1] * lc + c[2] * mu * mu + c[3] * lc * lc;      // eq. 95
+          const float cfh = c[4] * mu + c[5] * lc * mu;                              // eq. 99
+          const float cmr = c[10] * mu + c[11] * lc * mu;                            // eq. 101
+          const float avg = 0.5f * 1.225f * (om * Rp) * (om * Rp) * (3.14159265358979323846f * Rp * Rp);
+          const float fh = cfh * avg, ft = cft * avg, mz = cmr * avg * Rp * ((i & 1) ? 1.f : -1.f);  // direction (:1496)
+          const float fx = adv_cp * fh, fy = adv_sp * fh;                            // R_z(psi) (:1633-1641)
+          F0x += fx; F0y += fy; F0z += ft;
+          t0x += r.ry * ft - r.rz * fy; t0y += r.rz * fx - r.rx * ft; t0z += r.rx * fy - r.ry * fx + mz;
+        }
+        continue;
+      }
+      F0x = fmaf(T, r.ax, F0x); F0y = fmaf(T, r.ay, F0y); F0z = fmaf(T, r.az, F0z);
+      t0x = fmaf(T, r.mx, t0x); t0y = fmaf(T, r.my, t0y); t0z = fmaf(T, r.mz, t0z);
+      if (noisy && i < tp.n_u) {
+        const float nf = a.noise_f * nz[i], nm = a.noise_m * nz[6 + i] * tp.kf_over_km;
+        F0x = fmaf(nf, r.ax, F0x); F0y = fmaf(nf, r.ay, F0y); F0z = fmaf(nf, r.az, F0z);
+        t0x += nf * r.gx + nm * (r.mx - r.gx); t0y += nf * r.gy + nm * (r.my - r.gy); t0z += nf * r.gz + nm * (r.mz - r.gz);
+      }
+    }
+  };
+  if (!EXT) rotor_wrench(0);
   // drag coefficient x rotor speed sum: the first substep still sees the previously applied action (:532,:545)
   const float dk0 = -tp.drag_k[0], dk1 = -tp.drag_k[1], dk2 = -tp.drag_k[2];
 

@@ -331,6 +331,31 @@ def _assets_dirs(assets_dir: Optional[str]) -> List[str]:
 
 _cache: Dict[tuple, VehicleType] = {}
 
+_FROZEN_PROPS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "propeller_tables.json")
+ADVANCED_PROPELLER = "mamr-8x4.5"  # BaseAviary.py:1617
+
+
+def load_propeller(name: str = ADVANCED_PROPELLER) -> dict:
+    """The oblique-flow fit the "advanced" quad model evaluates (``Data_section5_ObliqueFlow[name]``,
+    dronesim/database/propeller_database.py:232-552; used by BaseAviary._get_prop_FMs :1617-1627 through
+    utils.calculate_propeller_forces_moments, method 2): 14 coefficients + the radius in metres
+    (``diameter_in / 2 * 0.0254``, utils/utils.py:172-174).  Read from the frozen table (tools/freeze_vehicle_tables.py)."""
+    with open(_FROZEN_PROPS) as f:
+        tab = json.load(f)
+    if name not in tab:
+        print("[ERROR] in load_propeller(), no table for propeller '%s'" % name)
+        raise KeyError(name)
+    return {"coeff": [float(x) for x in tab[name]["section5_oblique_flow"]],
+            "radius": float(tab[name]["diameter_in"]) / 2 * 0.0254}
+
+
+def as_advanced(vt: VehicleType) -> VehicleType:
+    """A copy of a quad type whose TYPE selects the oblique-flow propeller model ("advanced" in TYPE,
+    BaseAviary.py:1493).  No shipped URDF declares it; this is how a user (or a test) opts in."""
+    import dataclasses
+
+    return dataclasses.replace(vt, name=vt.name + "_advanced", TYPE=vt.TYPE + "_advanced")
+
 
 def load_vehicle(name: str, assets_dir: Optional[str] = None) -> VehicleType:
     """``name`` is what the reference passes in ``drone_model=[...]`` (URDF stem)."""

@@ -107,7 +107,9 @@ typedef struct ds_type_params {
   int32_t n_u;   /* INDI_ACTUATOR_NR */
   int32_t n_v;   /* INDI_OUTPUT_NR */
   int32_t law;   /* DS_LAW_* */
-  int32_t rotor_model; /* 0: quad, forces on links 0..n_u-1 + one base torque (BaseAviary.py:1477-1543); 1: morphing hexa (:1389-1457) */
+  int32_t rotor_model; /* 0: quad, forces on links 0..n_u-1 + one base torque (BaseAviary.py:1477-1543); 1: morphing hexa
+                          (:1389-1457); 2: quad whose TYPE carries "advanced": oblique-flow propeller model (:1493-1512,
+                          1570-1644; quaternion integrator only) */
   double mass;          /* M (literal) or whole-tree mass */
   double J[9];          /* row-major inertia about the centre of mass, body axes */
   double r_com[3];      /* centre of mass in the base frame */
@@ -131,6 +133,8 @@ typedef struct ds_type_params {
   double init_cmd;                      /* controller reset: 0.0 (INDIControl.py:129) / 0.5 (INDIControl_6DOF.py:234) */
   double init_thrust;                   /* 0.0 (INDIControl.py:127) / 0.3 (INDIControl_6DOF.py:232) */
   double max_speed_kmh;                 /* MAX_SPEED_KMH (BaseAviary.py:2079): SPEED_LIMIT of VelocityAviary.py:92-94 */
+  double adv_coeff[14];                 /* rotor_model 2: Data_section5_ObliqueFlow["mamr-8x4.5"] (propeller_database.py:537-552) */
+  double adv_radius;                    /* propeller radius in metres (utils/utils.py:172-174) */
 } ds_type_params;
 
 /* Where the controller's set-points come from. */

@@ -35,6 +35,8 @@ R7  ``_drag`` / ``_downwash`` forces act at the base-frame origin along LINK_FRA
     RECEIVING drone's coefficients.
 R8  integrator ``"quat"`` (beyond the reference, asked by north_star): Newton-Euler about the
     composite centre of mass, semi-implicit Euler, exponential-map quaternion update.
+R10 "advanced" quad types (``"advanced" in TYPE``, :1493): the oblique-flow propeller fit of ``_get_prop_FMs`` replaces
+    KF rpm^2 / KM rpm^2; pinned by ``tests/golden/rotor_tello_advanced.npz`` (the reference's own branch executed).
 R9  first-order motor model (beyond the reference, asked by north_star; off by default): per substep
     rpm += (1 - exp(-dt / tau)) (rpm_cmd - rpm); thrust / torque / ground effect use the actual rpm, drag the
     actual rpm sum before the substep's update.  tau = 0 is the reference's static map (:1487-1490).
@@ -103,6 +105,39 @@ def quat_exp(w, dt):
     return np.array([th[0] * k, th[1] * k, th[2] * k, math.cos(half)])
 
 
+def advanced_rotor_FMs(prop, quat, vel, rpm, rho=1.225):
+    """``BaseAviary._get_prop_FMs`` (BaseAviary.py:1570-1644) with ``utils.calculate_propeller_forces_moments``
+    method 2 (utils/utils.py:149-202, 343-416): per-rotor force and moment vectors in the body frame.
+    ``prop``: {"coeff": 14 numbers of Data_section5_ObliqueFlow, "radius": m}."""
+    (CsFT, k1, k2, k3, k4, k5, CsMQ, k6, k7, k8, k9, k10, k11, k12) = prop["coeff"]
+    Rp = prop["radius"]
+    R = p.rotmat(quat)
+    vel = np.asarray(vel, float)
+    V_i = vel if np.linalg.norm(vel) > 0.1 else np.array([0.1, 0.0, 0.0])  # :1585-1589
+    V_b = R.dot(V_i)  # (sic) the reference rotates with R, not its transpose (:1590)
+    V_b_normed = V_b / np.linalg.norm(V_b)
+    beta = np.arccos(V_b_normed.dot(np.array([0.0, 0.0, 1.0])))  # :1600-1602
+    psi = np.arctan(V_b[1] / V_b[0]) if V_b[0] > 0.1 else 0.0  # :1603-1605
+    V = np.linalg.norm(vel)  # the un-substituted speed (:1623)
+    F_b, M_b = [], []
+    R_z = np.array([[np.cos(psi), -np.sin(psi), 0.0], [np.sin(psi), np.cos(psi), 0.0], [0.0, 0.0, 1.0]])
+    for _rpm in rpm:
+        omega = _rpm / 60.0 * 2 * np.pi
+        omega = omega if omega > 10.0 else 10.0  # utils.py:176
+        mu = V * math.sin(beta) / (omega * Rp)  # utils.py:383-384
+        lambda_c = V * math.cos(beta) / (omega * Rp)
+        cft = CsFT + k1 * lambda_c + k2 * mu**2 + k3 * lambda_c**2  # eq. 95
+        cfh = k4 * mu + k5 * lambda_c * mu  # eq. 99
+        cmq = CsMQ + k6 * lambda_c + k7 * mu**2 + k8 * lambda_c**2  # eq. 100
+        cmr = k9 * mu + k10 * lambda_c * mu  # eq. 101
+        cmp_ = k11 * mu + k12 * lambda_c * mu  # eq. 102
+        avg = 0.5 * rho * (omega * Rp) ** 2 * math.pi * Rp**2  # utils.py:192-193
+        FM = np.array([cfh * avg, 0.0, cft * avg, cmp_ * avg * Rp, cmq * avg * Rp, cmr * avg * Rp])
+        F_b.append(R_z.dot(FM[:3]))
+        M_b.append(R_z.dot(FM[3:]))
+    return F_b, M_b
+
+
 def body_wrench(pp, cmd, cmd_prev_rpm_sum, pos, quat, rpy, vel, others_pos, gnd, drag, dw, rpm=None, noise=None):
     """Body-frame force and torque about the (composite) centre of mass for one substep.
     ``rpm``: actual rotor speeds when the first-order motor model (extension, R9) is on; default = the static map.
@@ -125,10 +160,22 @@ def body_wrench(pp, cmd, cmd_prev_rpm_sum, pos, quat, rpy, vel, others_pos, gnd,
                 F += lat
                 tau += np.cross(pp.rotor_pos[i] - pp.r_com, lat)
             tau += np.array([m_noise[0], m_noise[1], 0.0])
-    for i in range(pp.n_u):
-        f = T[i] * pp.rotor_axis[i]
-        F += f
-        tau += np.cross(pp.rotor_pos[i] - pp.r_com, f) + pp.spin[i] * Q[i] * pp.torque_axis[i]
+    if "advanced" in pp.vt.TYPE:
+        # _quad_copter_physics, "advanced" branch (:1493-1512): force F_prop[i] on rotor link i, torque
+        # [0, 0, M_prop[i][2] * direction[i]] on the same link, direction = [-1, 1, -1, 1]; no noise on this branch
+        from dronesim_b200.vehicles import load_propeller
+        F_b, M_b = advanced_rotor_FMs(load_propeller(), quat, vel, rpm)
+        direction = [-1.0, 1.0, -1.0, 1.0]
+        F = np.zeros(3)
+        tau = np.zeros(3)
+        for i in range(pp.n_u):
+            F += F_b[i]
+            tau += np.cross(pp.rotor_pos[i] - pp.r_com, F_b[i]) + np.array([0.0, 0.0, M_b[i][2] * direction[i]])
+    else:
+        for i in range(pp.n_u):
+            f = T[i] * pp.rotor_axis[i]
+            F += f
+            tau += np.cross(pp.rotor_pos[i] - pp.r_com, f) + pp.spin[i] * Q[i] * pp.torque_axis[i]
     if gnd:  # _groundEffect :1672-1699
         if abs(rpy[0]) < np.pi / 2 and abs(rpy[1]) < np.pi / 2:
             for i in range(pp.n_u):

@@ -19,6 +19,8 @@ three PyBullet math functions and an empty gym):
                                            with a recording stand-in for the module's ``p``)
                                         -> rotor_<vehicle>.npz (the LIVE ``_quad_copter_physics`` :1477-1543 /
                                            ``_morphing_hexa_physics`` :1389-1457, noise source zeroed)
+                                        -> rotor_tello_advanced.npz (the "advanced" branch :1493-1512 ->
+                                           ``_get_prop_FMs`` :1570-1644 -> utils.calculate_propeller_forces_moments)
 
 The fixtures are small .npz files; they are what travels to the GPU box (the reference does not).
 """
@@ -340,7 +342,41 @@ def rotor_fixture(name, seed, n_cases=24):
     return {k: np.array(v, float) for k, v in out.items()}
 
 
+def advanced_rotor_fixture(name, seed, n_cases=40):
+    """``_quad_copter_physics``'s "advanced" branch (BaseAviary.py:1493-1512) -> ``_get_prop_FMs`` (:1570-1644) ->
+    ``utils.calculate_propeller_forces_moments`` method 2, executed unbound for a quad whose TYPE carries "advanced"."""
+    import types
+    import warnings
+
+    import dronesim.envs.BaseAviary as BA
+    from dronesim_b200.vehicles import load_vehicle
+
+    vt = load_vehicle(name)
+    rng = np.random.default_rng(seed)
+    rec = _RecordingBullet()
+    BA.p = rec
+    drone = types.SimpleNamespace(PWM2RPM_SCALE=np.array(vt.PWM2RPM_SCALE), PWM2RPM_CONST=np.array(vt.PWM2RPM_CONST),
+                                  KF=vt.KF, KM=vt.KM, INDI_ACTUATOR_NR=4, TYPE=vt.TYPE + "_advanced")
+    out = dict(cmd=[], quat=[], vel=[], force_link=[], force=[], torque_link=[], torque=[])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # the model warns beyond mu / lambda = 0.3 (utils.py:386-396)
+        for c in range(n_cases):
+            cmd = rng.uniform(0.2, 1.0, 4)
+            quat = np.array(pyb_math.getQuaternionFromEuler(rng.uniform(-0.5, 0.5, 3)))
+            vel = rng.normal(0, [0.02, 1.5, 4.0][c % 3], 3)  # below the 0.1 m/s substitution, moderate, fast
+            self = types.SimpleNamespace(drones=[drone], DRONE_IDS=[1], CLIENT=0, quat=np.array([quat]), vel=np.array([vel]))
+            self._get_prop_FMs = lambda rpm, n, _s=self: BA.BaseAviary._get_prop_FMs(_s, rpm, n)
+            rec.forces, rec.torques = [], []
+            BA.BaseAviary._quad_copter_physics(self, cmd, 0)
+            for k, v in (("cmd", cmd), ("quat", quat), ("vel", vel), ("force_link", [l for l, _, _ in rec.forces]),
+                         ("force", [f for _, f, _ in rec.forces]), ("torque_link", [l for l, _, _ in rec.torques]),
+                         ("torque", [t for _, t, _ in rec.torques])):
+                out[k].append(np.array(v, float))
+    return {k: np.array(v) for k, v in out.items()}
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "rotor_tello_advanced.npz"), **advanced_rotor_fixture("tello", seed=600))
     for i, name in enumerate(["robobee", "tello", "hexa_6DOF", "hexa_6DOF_simple"]):
         np.savez_compressed(os.path.join(HERE, "rotor_%s.npz" % name), **rotor_fixture(name, seed=500 + i))
     for i, name in enumerate(["robobee", "tello"]):

@@ -14,6 +14,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from helpers import angle_between, core_state, make_pair  # noqa: E402
+from oracle.sim import OracleSwarm  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 POS_TOL = 1e-4  # m
@@ -667,3 +668,41 @@ def test_rotor_noise_stream_parity_and_sharding():
     c.step(c.targets_per_vehicle(tgt[2 * D:]), 24)
     np.testing.assert_array_equal(core_state(c)["pos"], noisy[2 * D:])
     c.close()
+
+
+# ------------------------------------------------------------------------------------------
+# the oblique-flow propeller model ("advanced" quad types) - a few substeps with external actions
+# against the oracle, which is pinned to the reference's own branch (tests/test_oracle_dynamics.py)
+# ------------------------------------------------------------------------------------------
+def test_advanced_propeller_model_physics():
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.vehicles import as_advanced, load_vehicle
+
+    vt = as_advanced(load_vehicle("tello"))
+    E, K = 24, 2
+    core = SwarmCore([vt], E, integrator="quat", composite=True, aggregate_phy_steps=K, drag=True)
+    orc = OracleSwarm([vt], E, integrator="quat", composite=True, drag=True, aggregate_phy_steps=K)
+    rng = np.random.default_rng(31)
+    pos0 = rng.uniform(-1, 1, (E, 1, 3)) + [0, 0, 3.0]
+    rpy0 = rng.uniform(-0.4, 0.4, (E, 1, 3))
+    vel0 = rng.normal(0, 1.0, (E, 1, 3)) * np.array([0.03, 1.0, 3.0])[np.arange(E) % 3][:, None, None]
+    core.reset(pos0, rpy0=rpy0, vel0=vel0)
+    orc.reset(pos0, rpy0=rpy0, vel0=vel0)
+    for _ in range(3):
+        act = np.zeros((E, 1, 6))
+        act[:, 0, :4] = rng.uniform(0.02, 0.12, (E, 4))  # the 8-inch propeller fit at Tello rpm: keep the thrust flyable
+        core.physics_step(torch.tensor(act.reshape(E, 6), dtype=torch.float32, device="cuda"))
+        orc.physics_step(act)
+    st = core_state(core)
+    np.testing.assert_allclose(st["pos"], orc.pos.reshape(E, 3), atol=2e-5)
+    np.testing.assert_allclose(st["vel"], orc.vel.reshape(E, 3), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(st["omega_body"], orc.rates.reshape(E, 3), rtol=1e-3, atol=2e-3)
+    assert angle_between(st["quat"], orc.quat.reshape(E, 4)).max() <= 2e-5
+    # the model matters: a plain tello (KF rpm^2) ends elsewhere
+    plain = SwarmCore(["tello"], E, integrator="quat", composite=True, aggregate_phy_steps=K, drag=True)
+    plain.reset(pos0, rpy0=rpy0, vel0=vel0)
+    plain.physics_step(torch.tensor(act.reshape(E, 6), dtype=torch.float32, device="cuda"))
+    assert np.abs(core_state(plain)["vel"] - st["vel"]).max() > 1e-2
+    core.close()
+    plain.close()

@@ -95,3 +95,29 @@ def test_rotor_forces_vs_live_reference_functions(name):
         tq = tq + (sum(g["torque"][c][j, 2] * pp.torque_axis[j] for j in range(n_u)) if hexa else g["torque"][c][0])
         np.testing.assert_allclose(F, Fx, rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(tau, tq, rtol=1e-10, atol=1e-14)
+
+
+def test_advanced_propeller_model_vs_reference_branch():
+    """SURVEY 8f row 4: the oblique-flow propeller model ("advanced" in TYPE, BaseAviary.py:1493-1512, 1570-1644;
+    utils/utils.py:149-202, 343-416) against the reference's own branch executed (rotor_tello_advanced.npz)."""
+    from dronesim_b200.vehicles import as_advanced, load_propeller
+
+    g = np.load(os.path.join(GOLD, "rotor_tello_advanced.npz"))
+    vt = as_advanced(load_vehicle("tello"))
+    assert "advanced" in vt.TYPE and vt.INDI_ACTUATOR_NR == 4
+    pp = od.PhysParams(vt, composite=True)
+    prop = load_propeller()
+    assert len(prop["coeff"]) == 14 and abs(prop["radius"] - 0.1016) < 1e-12
+    for c in range(g["cmd"].shape[0]):
+        rpm = od.rpm_of_cmd(pp, g["cmd"][c])
+        F_b, M_b = od.advanced_rotor_FMs(prop, g["quat"][c], g["vel"][c], rpm)
+        np.testing.assert_array_equal(g["force_link"][c], [0, 1, 2, 3])
+        np.testing.assert_array_equal(g["torque_link"][c], [0, 1, 2, 3])
+        np.testing.assert_allclose(np.array(F_b), g["force"][c], rtol=1e-12, atol=1e-15)
+        direction = np.array([-1.0, 1.0, -1.0, 1.0])
+        np.testing.assert_allclose(np.array([m[2] for m in M_b]) * direction, g["torque"][c][:, 2], rtol=1e-12, atol=1e-16)
+        assert not g["torque"][c][:, :2].any()
+        F, tau, _ = od.body_wrench(pp, g["cmd"][c], 0.0, np.zeros(3), g["quat"][c], np.zeros(3), g["vel"][c], [], False, False, False)
+        np.testing.assert_allclose(F, g["force"][c].sum(axis=0), rtol=1e-12)
+        tq = sum(np.cross(pp.rotor_pos[i] - pp.r_com, g["force"][c][i]) + g["torque"][c][i] for i in range(4))
+        np.testing.assert_allclose(tau, tq, rtol=1e-10, atol=1e-14)

@@ -22,3 +22,15 @@ if __name__ == "__main__":
     with open(dst, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote", os.path.normpath(dst))
+    # the one propeller the "advanced" quad model uses (BaseAviary.py:1617: propeller = "mamr-8x4.5", lower-order
+    # oblique-flow fit): its 14 coefficients from the reference's database module, as data
+    ref_root = os.path.normpath(os.path.join(assets, "..", ".."))
+    sys.path.insert(0, ref_root)
+    from dronesim.database.propeller_database import Data_section5_ObliqueFlow  # noqa: E402
+
+    props = {"mamr-8x4.5": {"section5_oblique_flow": [float(x) for x in Data_section5_ObliqueFlow["mamr-8x4.5"]],
+                            "diameter_in": 8.0}}
+    dst2 = os.path.join(os.path.dirname(dst), "propeller_tables.json")
+    with open(dst2, "w") as f:
+        json.dump(props, f, indent=1, sort_keys=True)
+    print("wrote", os.path.normpath(dst2))

@@ -706,3 +706,47 @@ def test_advanced_propeller_model_physics():
     assert np.abs(core_state(plain)["vel"] - st["vel"]).max() > 1e-2
     core.close()
     plain.close()
+
+
+# ------------------------------------------------------------------------------------------
+# error behaviour of the C ABI: status codes, never an exception across the boundary, never a silent fallback
+# ------------------------------------------------------------------------------------------
+def test_abi_error_codes_on_device():
+    _need_gpu()
+    import ctypes as C
+
+    from dronesim_b200 import _lib as L
+    from dronesim_b200.core import SwarmCore
+
+    lib = L.lib()
+    # stepping before reset -> DS_ERR_STATE
+    core = SwarmCore(["robobee"], 4)
+    t = L.ds_targets()
+    assert lib.ds_step(core._h, C.byref(t), 1, 0, None) == L.DS_ERR_STATE
+    core.reset(np.zeros((4, 3)))
+    # missing target pointer / unknown mode / bad order -> DS_ERR_INVALID
+    assert lib.ds_step(core._h, C.byref(t), 1, 0, None) == L.DS_ERR_INVALID
+    t.mode = 9
+    assert lib.ds_step(core._h, C.byref(t), 1, 0, None) == L.DS_ERR_INVALID
+    good = core.targets_per_vehicle(np.zeros((4, 4)))
+    assert lib.ds_step(core._h, C.byref(good), 1, 7, None) == L.DS_ERR_INVALID
+    assert lib.ds_step(core._h, C.byref(good), 1, 0, None) == L.DS_OK
+    assert lib.ds_physics_step(core._h, None, None) == L.DS_ERR_INVALID
+    assert lib.ds_log_attach(core._h, (C.c_int32 * 1)(99), 1, 8) == L.DS_ERR_INVALID  # vehicle id out of range
+    core.close()
+    # extensions need the quaternion integrator; the rate / thrust entry needs the quad law
+    cfg = L.ds_config()
+    cfg.n_envs, cfg.drones_per_env, cfg.substeps, cfg.sim_freq, cfg.gravity = 1, 1, 1, 240.0, 9.8
+    cfg.integrator, cfg.motor_tau = L.DS_INTEG_RPY, 0.05
+    h = C.c_void_p()
+    assert lib.ds_create(C.byref(cfg), C.byref(h)) == L.DS_ERR_UNSUPPORTED and not h.value
+    cfg.motor_tau, cfg.drones_per_env = 0.0, 33
+    assert lib.ds_create(C.byref(cfg), C.byref(h)) == L.DS_ERR_UNSUPPORTED
+    cfg.drones_per_env, cfg.n_envs = 1, 0
+    assert lib.ds_create(C.byref(cfg), C.byref(h)) == L.DS_ERR_INVALID
+    hexa = SwarmCore(["hexa_6DOF"], 2)
+    hexa.reset(np.zeros((2, 3)) + [0, 0, 1.0])
+    rt = hexa.targets_rate_thrust(np.zeros((2, 4)))
+    assert lib.ds_step(hexa._h, C.byref(rt), 1, 1, None) == L.DS_ERR_UNSUPPORTED
+    assert lib.ds_strerror(L.DS_ERR_UNSUPPORTED).decode() == "unsupported configuration"
+    hexa.close()

@@ -376,6 +376,10 @@ static void base_args(const ds_handle* h, DsArgs& a) {
 
 static int set_targets(DsArgs& a, const ds_targets* t) {
   if (!t) return DS_ERR_INVALID;
+  // rows are float4 / staged by 16-byte bulk copies: every array must be 16-byte aligned
+  const void* ptrs[] = {t->pos_yaw, t->vel, t->acc, t->table, t->offset};
+  for (const void* p : ptrs)
+    if (((uintptr_t)p & 15u) != 0) return DS_ERR_INVALID;
   a.tmode = t->mode;
   if (t->mode == 0) {
     if (!t->pos_yaw) return DS_ERR_INVALID;

@@ -137,7 +137,7 @@ typedef struct ds_type_params {
   double adv_radius;                    /* propeller radius in metres (utils/utils.py:172-174) */
 } ds_type_params;
 
-/* Where the controller's set-points come from. */
+/* Where the controller's set-points come from.  Every array is 16-byte aligned (rows are float4; DS_ERR_INVALID otherwise). */
 typedef struct ds_targets {
   int32_t mode;          /* 0: per-vehicle device arrays; 1: shared waypoint table + per-vehicle counter;
                             2: velocity command (VelocityAviary._preprocessAction, VelocityAviary.py:221-264): `vel`

@@ -354,7 +354,7 @@ def run_ours(args):
     hbm_achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "ds_step_kernel<QUAT, DW=symmetric16, NU6, WARPSYNC, FUSED, FX=ground+drag>",
+                "kernel": "ds_step_kernel<QUAT, DW=symmetric16, NU6, WARPSYNC, FUSED, FX=ground+drag, EXT=off>",
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "algorithmic_bytes_per_vehicle_control_step": hetero16_bytes_per_control_step()}
     prof = os.path.join(ROOT, "profiles", "roofline_inputs.json")

@@ -750,3 +750,33 @@ def test_abi_error_codes_on_device():
     assert lib.ds_step(hexa._h, C.byref(rt), 1, 1, None) == L.DS_ERR_UNSUPPORTED
     assert lib.ds_strerror(L.DS_ERR_UNSUPPORTED).decode() == "unsupported configuration"
     hexa.close()
+
+
+def test_max_drones_per_env_downwash():
+    """DS_MAX_DRONES_PER_ENV = 32 drones in one env (one env per warp, ordered-pair downwash), mixed types, vs the oracle."""
+    _need_gpu()
+    models = (["robobee", "hexa_6DOF", "tello", "hexa_6DOF_simple"] * 8)[:32]
+    D, E, K = 32, 2, 4
+    core, orc = make_pair(models, E, "quat", K=K, gnd=True, drag=True, dw=True, radius=2.0)
+    rng = np.random.default_rng(41)
+    pos0 = np.zeros((E, D, 3))
+    for s_ in range(D):
+        pos0[:, s_] = [1.5 * (s_ % 8), 1.5 * (s_ // 16), 2.0 + 0.7 * ((s_ // 8) % 2)]
+    pos0 += rng.uniform(-0.02, 0.02, pos0.shape)
+    act0 = np.zeros((E, D, 6))
+    for s_, m in enumerate(models):
+        act0[:, s_, : (6 if "hexa" in m else 4)] = 0.45
+    core.reset(pos0, action0=act0)
+    orc.reset(pos0)
+    tgt = core.targets_per_vehicle(np.concatenate([pos0.reshape(-1, 3), np.zeros((E * D, 1))], axis=1))
+    act = act0.copy()
+    for step in range(15):  # 0.25 s
+        core.step(tgt, 1)
+        orc.physics_step(act)
+        act = orc.control_step(pos0)
+    _compare_state(core, orc, what="D=32")
+    _, nb, _, _ = core.get_obs()
+    got = nb.cpu().numpy().astype(np.uint32).reshape(E, D)
+    exp = orc.adjacency_bits()
+    assert (got == exp).mean() > 0.99 and ((got >> np.arange(D, dtype=np.uint32)) & 1).all()  # 32-bit rows, self bit set
+    core.close()

@@ -138,6 +138,24 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(self.power) if self.power else None}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs closest to its GPU (NVML's ideal affinity) so that the pinned host buffers of the
+    end-to-end path are allocated on that NUMA node: with one process per GPU the H2D copies of the ranks then do not
+    all cross the same socket interconnect.  Best effort - returns a description or None."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[index]) if vis else index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return "cpus %d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+    except Exception as e:  # no NVML / not permitted: keep the inherited affinity
+        return "unbound (%s)" % type(e).__name__
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -199,6 +217,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # pinned staging buffers are first-touched on the GPU's own NUMA node
     if world > 1:
         # keep stdout for the ONE JSON line: NCCL's own log lines (e.g. its version banner) go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -267,7 +286,7 @@ def run_ours(args):
         e2e_s = max_over_ranks(t1 - t0)
         e2e = {"value": N * n_gpus * K * e2e_steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(N * 16 * n_gpus), "d2h_bytes_per_step": int(E * n_gpus),
-               "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+               "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "host_affinity": numa,
                "call": "ds_rollout_host (%d control steps per call): per step, pinned targets [N][4] f32 -> HBM on a copy "
                        "stream, fused step, per-env done u8 -> pinned host; copies overlap the previous / next step's "
                        "compute; synchronised at the end of each call" % chunk}
@@ -406,6 +425,11 @@ def run_ours(args):
         from oracle.cpu_bench import time_oracle
 
         cores = os.cpu_count() or 1
+        try:  # the GPU-side NUMA binding must not shrink the CPU arm: its workers inherit this process's affinity
+            os.sched_setaffinity(0, range(cores))
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            pass
         n_cpu = args.cpu_steps
         if n_cpu <= 0:  # bounded sample: ~12 s of CPU work, sized from a 2-step calibration
             cal = time_oracle(steps=2, warmup=1, workers=cores, envs_per_worker=1)

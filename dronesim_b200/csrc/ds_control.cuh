@@ -79,7 +79,7 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
   // ---- attitude: Euler angles and the rotation matrix the reference's G is built from
   const float x = s.qx, y = s.qy, z = s.qz, w = s.qw;
   float d = x * x + y * y + z * z + w * w;
-  Mat3 R = ds_rot(x, y, z, w, 2.0f / d);
+  Mat3 R = ds_rot(x, y, z, w, 2.0f * ds_rcp(d));  // |q|^2 = 1 up to rounding: the 1-ulp MUFU reciprocal is exact enough
   float sarg = -2.0f * (x * z - w * y);
   const bool gimbal = (sarg <= -DS_GIMBAL) || (sarg >= DS_GIMBAL);
   float A_r = 2.0f * (y * z + w * x), B_r = w * w - x * x - y * y + z * z;
@@ -88,7 +88,11 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
   Mat3 Re = R;  // rotation matrix of the extracted Euler angles (== R unless gimbal branch)
   float phi = 0.f, theta = 0.f, psi = 0.f;
   const bool need_angles = (!six) || want_yaw_err || gimbal;
-  if (need_angles) ds_euler(x, y, z, w, phi, theta, psi);
+#ifdef DS_EXACT_CTRL_TRIG
+  if (need_angles) ds_euler<false>(x, y, z, w, phi, theta, psi);
+#else
+  if (need_angles) ds_euler<true>(x, y, z, w, phi, theta, psi);
+#endif
   if (!gimbal) {
     cphi = B_r * rsqrtf(A_r * A_r + B_r * B_r);
     float ny = rsqrtf(A_y * A_y + B_y * B_y);
@@ -113,12 +117,16 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
 
   if (!six) {
     float dphi = -u1 * (1.0f / T);
-    float dtheta = u0 / (T * cphi);
+    float dtheta = u0 * ds_rcp(T * cphi);
     float yaw_inc = ds_norm_ang(t.yaw - psi);  // :341
     float te_r = phi + dphi, te_p = theta + dtheta, te_y = psi + yaw_inc;
     o.yaw_err = te_y - psi;  // :227
     // ---- attitude loop (INDIControl.py:388-402)
-    float4 tq = ds_quat_from_euler(te_r, te_p, te_y);
+#ifdef DS_EXACT_CTRL_TRIG
+    float4 tq = ds_quat_from_euler<false>(te_r, te_p, te_y);
+#else
+    float4 tq = ds_quat_from_euler<true>(te_r, te_p, te_y);
+#endif
     float ew = w * tq.w + x * tq.x + y * tq.y + z * tq.z;  // utils/math.py:23-31
     float ex = w * tq.x - x * tq.w - y * tq.z + z * tq.y;
     float ey = w * tq.y + x * tq.z - y * tq.w - z * tq.x;

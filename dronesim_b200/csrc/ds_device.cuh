@@ -160,24 +160,62 @@ __device__ __forceinline__ float ds_norm_ang(float x) {
   return x;
 }
 
-// pybullet getEulerFromQuaternion (oracle/pyb_math.py); returns gimbal flag
+// atan2 in ~20 instructions: min / max ratio through one MUFU reciprocal, degree-8 polynomial in t^2 on [0, 1]
+// (least-squares Chebyshev fit of atan(t) / t; 1.1e-7 max absolute error evaluated in FP32), quadrant fix-ups by
+// selects.  Total error <= 2e-7 rad, the same order as libm's atan2f (2 ulp); used by the controller only.
+__device__ __forceinline__ float ds_atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = mn * ds_rcp(mx);
+  const float s = t * t;
+  float p = 0.0028340641874819994f;
+  p = fmaf(p, s, -0.016005029901862144f); p = fmaf(p, s, 0.042587608098983765f); p = fmaf(p, s, -0.07495445758104324f);
+  p = fmaf(p, s, 0.10636754333972931f);   p = fmaf(p, s, -0.14202570915222168f); p = fmaf(p, s, 0.19992484152317047f);
+  p = fmaf(p, s, -0.3333306610584259f);   p = fmaf(p, s, 1.0f);
+  p *= t;
+  p = (ay > ax) ? (0.5f * DS_PI_F - p) : p;
+  p = (x < 0.f) ? (DS_PI_F - p) : p;
+  p = (mx == 0.f) ? 0.f : p;  // atan2(0, 0)
+  return copysignf(p, y);
+}
+
+// pybullet getEulerFromQuaternion (oracle/pyb_math.py); returns gimbal flag.  FAST: the controller's variant
+// (ds_atan2_fast; asin(s) = atan2(s, sqrt((1 - s)(1 + s))), |s| < 0.99999 here); the state vector / integrator use libm.
+template <bool FAST = false>
 __device__ __forceinline__ bool ds_euler(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
   float sarg = -2.0f * (x * z - w * y);
   if (sarg <= -DS_GIMBAL) { roll = 0.f; pitch = -0.5f * DS_PI_F; yaw = 2.0f * atan2f(x, -y); return true; }
   if (sarg >= DS_GIMBAL)  { roll = 0.f; pitch = 0.5f * DS_PI_F;  yaw = 2.0f * atan2f(-x, y); return true; }
   float sqx = x * x, sqy = y * y, sqz = z * z, squ = w * w;
-  roll = atan2f(2.0f * (y * z + w * x), squ - sqx - sqy + sqz);
-  pitch = asinf(sarg);
-  yaw = atan2f(2.0f * (x * y + w * z), squ + sqx - sqy - sqz);
+  if (FAST) {
+    roll = ds_atan2_fast(2.0f * (y * z + w * x), squ - sqx - sqy + sqz);
+    const float c2 = (1.0f - sarg) * (1.0f + sarg);
+    pitch = ds_atan2_fast(sarg, c2 * ds_rsqrt(c2));
+    yaw = ds_atan2_fast(2.0f * (x * y + w * z), squ + sqx - sqy - sqz);
+  } else {
+    roll = atan2f(2.0f * (y * z + w * x), squ - sqx - sqy + sqz);
+    pitch = asinf(sarg);
+    yaw = atan2f(2.0f * (x * y + w * z), squ + sqx - sqy - sqz);
+  }
   return false;
 }
 
-// pybullet getQuaternionFromEuler
+// pybullet getQuaternionFromEuler.  FAST: the half-angle sines / cosines through MUFU.SIN / MUFU.COS (__sincosf, absolute
+// error 2^-21.4 for |half angle| <= pi) - used for the controller's target quaternion only, where a 1e-6 quaternion error
+// moves the command by < 4e-7 PWM (sensitivity = |pinv(G1/0.05)| rate_gain att_gain); the
+// integrator path (DS_INTEG_RPY) keeps the libm version.
+template <bool FAST = false>
 __device__ __forceinline__ float4 ds_quat_from_euler(float r, float p, float y) {
   float sph, cph, sth, cth, sps, cps;
-  sincosf(0.5f * r, &sph, &cph);
-  sincosf(0.5f * p, &sth, &cth);
-  sincosf(0.5f * y, &sps, &cps);
+  if (FAST) {
+    __sincosf(0.5f * r, &sph, &cph);
+    __sincosf(0.5f * p, &sth, &cth);
+    __sincosf(0.5f * y, &sps, &cps);
+  } else {
+    sincosf(0.5f * r, &sph, &cph);
+    sincosf(0.5f * p, &sth, &cth);
+    sincosf(0.5f * y, &sps, &cps);
+  }
   float4 q;
   q.x = sph * cth * cps - cph * sth * sps;
   q.y = cph * sth * cps + sph * cth * sps;

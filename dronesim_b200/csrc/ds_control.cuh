@@ -98,9 +98,9 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
     float ny = rsqrtf(A_y * A_y + B_y * B_y);
     cpsi = B_y * ny; spsi = A_y * ny;
   } else {  // roll = 0, pitch = +-pi/2: rebuild the matrix from the branch's angles
-    float sth, cth;
-    sincosf(theta, &sth, &cth);
-    sincosf(psi, &spsi, &cpsi);
+    float sth, cth;  // MUFU sin / cos: this rare branch must not drag libm's argument-reduction slow path into the kernel
+    __sincosf(theta, &sth, &cth);
+    __sincosf(psi, &spsi, &cpsi);
     cphi = 1.f;
     Re.m00 = cth * cpsi; Re.m10 = cth * spsi; Re.m20 = -sth;
     Re.m01 = -spsi;      Re.m11 = cpsi;       Re.m21 = 0.f;

@@ -42,9 +42,11 @@ __device__ __forceinline__ void ds_quat_step(float& qx, float& qy, float& qz, fl
     k = 0.5f + h2 * (-0.5f / 6.0f + h2 * (0.5f / 120.0f + h2 * (-0.5f / 5040.0f)));
     c = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f))));
   } else {
+    // |w| dt >= 1 rad per substep (>= 240 rad/s): a blown-up state; MUFU sin / cos keep it finite and this branch free
+    // of libm's argument-reduction slow path (two CALLs inside the substep loop otherwise)
     float half = sqrtf(h2), s;
-    sincosf(half, &s, &c);
-    k = 0.5f * s / half;
+    __sincosf(half, &s, &c);
+    k = 0.5f * s * ds_rcp(half);
   }
   float dx = tx * k, dy = ty * k, dz = tz * k, dw = c;
   float nx = qw * dx + qx * dw + qy * dz - qz * dy;

@@ -184,8 +184,8 @@ __device__ __forceinline__ float ds_atan2_fast(float y, float x) {
 template <bool FAST = false>
 __device__ __forceinline__ bool ds_euler(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
   float sarg = -2.0f * (x * z - w * y);
-  if (sarg <= -DS_GIMBAL) { roll = 0.f; pitch = -0.5f * DS_PI_F; yaw = 2.0f * atan2f(x, -y); return true; }
-  if (sarg >= DS_GIMBAL)  { roll = 0.f; pitch = 0.5f * DS_PI_F;  yaw = 2.0f * atan2f(-x, y); return true; }
+  if (sarg <= -DS_GIMBAL) { roll = 0.f; pitch = -0.5f * DS_PI_F; yaw = 2.0f * (FAST ? ds_atan2_fast(x, -y) : atan2f(x, -y)); return true; }
+  if (sarg >= DS_GIMBAL)  { roll = 0.f; pitch = 0.5f * DS_PI_F;  yaw = 2.0f * (FAST ? ds_atan2_fast(-x, y) : atan2f(-x, y)); return true; }
   float sqx = x * x, sqy = y * y, sqz = z * z, squ = w * w;
   if (FAST) {
     roll = ds_atan2_fast(2.0f * (y * z + w * x), squ - sqx - sqy + sqz);

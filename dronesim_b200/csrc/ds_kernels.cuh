@@ -156,7 +156,7 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsT
     float n2 = q.x * q.x + q.y * q.y + q.z * q.z;
     float k = (n2 != 0.f) ? tp.speed_limit * fabsf(q.w) / sqrtf(n2) : 0.f;
     float roll, pitch, yaw;
-    ds_euler(cs.qx, cs.qy, cs.qz, cs.qw, roll, pitch, yaw);
+    ds_euler<true>(cs.qx, cs.qy, cs.qz, cs.qw, roll, pitch, yaw);  // the controller's (libm-free) variant
     t.x = cs.px; t.y = cs.py; t.z = cs.pz; t.yaw = yaw;  // hold position and yaw (state[0:3], state[9])
     t.vx = k * q.x; t.vy = k * q.y; t.vz = k * q.z;
     t.ax = t.ay = t.az = 0.f;

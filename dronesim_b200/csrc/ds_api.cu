@@ -34,6 +34,11 @@ struct ds_handle {
   float4 *s_r0 = nullptr, *s_af = nullptr;  // extension state: rotor speeds, filtered angular acceleration
   float2* s_r1 = nullptr;
   bool ext = false;
+  int* d_wls_count = nullptr;   // [2] alternating per step (the fix-up kernel of step i re-arms the counter of step i + 1)
+  int* d_wls_index = nullptr;   // [n]
+  float* d_wls_nu = nullptr;    // [n][6]
+  int wls_phase = 0;
+  float* d_cmd_scratch = nullptr;  // [n][6]: un-fused control -> physics hand-over (order 1 with 6-DOF types)
   DsTypeDev* d_types = nullptr;
   DsWlsDev* d_wls = nullptr;
   uint8_t* d_slot_type = nullptr;
@@ -85,7 +90,8 @@ static void free_all(ds_handle* h) {
   void* ptrs[] = {h->s_pos, h->s_quat, h->s_vel, h->s_om, h->s_lv, h->s_lr, h->s_c0, h->s_a0, h->s_c1, h->s_a1,
                   h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
-                  h->d_roll_done[1], h->d_log_ids, h->d_log_states, h->s_r0, h->s_r1, h->s_af};
+                  h->d_roll_done[1], h->d_log_ids, h->d_log_states, h->s_r0, h->s_r1, h->s_af, h->d_wls_count, h->d_wls_index, h->d_wls_nu,
+                  h->d_cmd_scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; ++b) {
@@ -268,6 +274,12 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     h->slot_type[s] = slot_type[s];
   }
   h->n_types = n_types;
+  if (h->any_6dof && !h->d_wls_count) {  // deferred WLS slow path (ds_wls_fixup_kernel)
+    CK(cudaMalloc((void**)&h->d_wls_count, 2 * sizeof(int)));
+    CK(cudaMemset(h->d_wls_count, 0, 2 * sizeof(int)));
+    CK(cudaMalloc((void**)&h->d_wls_index, (size_t)h->n * sizeof(int)));
+    CK(cudaMalloc((void**)&h->d_wls_nu, (size_t)h->n * 6 * sizeof(float)));
+  }
   if (need_ext && !h->ext) {
     const size_t np = (size_t)h->n_pad;
     CK(cudaMalloc((void**)&h->s_r0, np * 16)); CK(cudaMalloc((void**)&h->s_r1, np * 8)); CK(cudaMalloc((void**)&h->s_af, np * 16));
@@ -435,13 +447,33 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   a.inv_ctrl_dt = h->cfg.sim_freq / (float)h->cfg.substeps;
   set_filter(h, a);
   cudaStream_t st = (cudaStream_t)stream;
+  if (order == DS_ORDER_CONTROL_THEN_PHYSICS && h->any_6dof) {
+    // The fused kernel defers the rare FP64 WLS iterations to a follow-up kernel, which is too late when the physics of
+    // the SAME launch needs the command: run the control kernel (in-line slow path), then the physics with its output.
+    if (!h->d_cmd_scratch) CK(cudaMalloc((void**)&h->d_cmd_scratch, (size_t)h->n * 6 * sizeof(float)));
+    for (int i = 0; i < n_control_steps; ++i) {
+      rc = ds_control_step(h, tgt, a.ctrl_dt, h->d_cmd_scratch, nullptr, nullptr, stream);
+      if (rc != DS_OK) return rc;
+      rc = ds_physics_step(h, h->d_cmd_scratch, stream);
+      if (rc != DS_OK) return rc;
+      h->act_valid = false;  // obs tail = the controller command (which is the action just applied)
+    }
+    return DS_OK;
+  }
   for (int i = 0; i < n_control_steps; ++i) {
     a.use_act = (h->first_action_pending && order == 0) ? 1 : 0;
     a.step0 = (uint32_t)h->step_counter;  // substep index of k = 0 (noise stream counter)
     a.store_act = 0;
+    a.wls_count = h->d_wls_count ? h->d_wls_count + h->wls_phase : nullptr;
+    a.wls_index = h->d_wls_index; a.wls_nu = h->d_wls_nu;
     time_flags(h, a);
     launch_step<0>(h, a, st);
     h->launches++;
+    if (h->any_6dof) {  // solve what the step kernel queued; re-arm the other counter for the next step
+      ds_wls_fixup_kernel<<<grid_for(h, 1 << 20, 1), 128, 0, st>>>(a, h->d_wls_count + (h->wls_phase ^ 1));
+      h->launches++;
+      h->wls_phase ^= 1;
+    }
     h->first_action_pending = false;
     h->act_valid = false;
     h->step_counter += h->cfg.substeps;  // BaseAviary.py:554

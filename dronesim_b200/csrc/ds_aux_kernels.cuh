@@ -213,6 +213,46 @@ __global__ void __launch_bounds__(256) ds_reset_kernel(const DsResetArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// deferred WLS slow path: the problems the fused kernel queued (first iterate outside the +-1.0 slack, wls_alloc.py:264),
+// one per thread: FP64 active-set solution, cmd = clip(cmd + du) (INDIControl_6DOF.py:630-631); the fused kernel held
+// the command of these vehicles, and nothing reads it before the next step's physics.  Also re-arms the OTHER counter.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ds_wls_fixup_kernel(const DsArgs a, int* next_count) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+  const int n = *a.wls_count;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const int v = a.wls_index[q];
+    const int type_id = a.slot_type[v % a.D];
+    const DsTypeDev& tp = a.types[type_id];
+    const DsWlsDev* P = a.wls + type_id;
+    const float4 C0 = a.s_c0[v];
+    const float2 C1 = a.s_c1[v];
+    const float cmd[6] = {C0.x, C0.y, C0.z, C0.w, C1.x, C1.y};
+    double vv[6], umin[6], umax[6], u[6];
+    for (int i = 0; i < 6; ++i) {
+      vv[i] = (double)a.wls_nu[(size_t)v * 6 + i];
+      umin[i] = P->pmin[i] - (double)cmd[i];
+      umax[i] = P->pmax[i] - (double)cmd[i];
+      u[i] = 0.0;
+    }
+    const int it = ds_wls_alloc(P, vv, umin, umax, u);
+    float out[6];
+    int sat = 0;
+    for (int i = 0; i < 6; ++i) {
+      const float c = cmd[i] + ((it > 0) ? (float)u[i] : 0.f);  // non-convergence: hold the command
+      out[i] = ds_clampf(c, tp.rotor[i].pmin, tp.rotor[i].pmax);
+      sat += (out[i] != c);
+    }
+    a.s_c0[v] = make_float4(out[0], out[1], out[2], out[3]);
+    a.s_c1[v] = make_float2(out[4], out[5]);
+    if (a.flags & 8u) {
+      if (sat) atomicAdd(a.stats + ST_SAT, (double)sat);
+      if (it < 0) atomicAdd(a.stats + ST_WLS_FAIL, 1.0);
+    }
+  }
+}
+
 // extension state after reset: rotor speeds of the all-zero action, filter state zero
 __global__ void __launch_bounds__(256) ds_reset_ext_kernel(const DsResetArgs a, float4* s_r0, float2* s_r1, float4* s_af) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n_pad; v += gridDim.x * blockDim.x) {

@@ -59,10 +59,21 @@ __device__ __forceinline__ void ds_rate_loop(const DsTypeDev& tp, const CtrlStat
   nu[2] = (rsp_r - s.wz) * tp.rate[2] - aaz;
 }
 
-template <bool NU6, bool EXT>
+// Where a lane whose first WLS iterate is infeasible (wls_alloc.py:264) sends its problem when the FP64 active-set loop
+// does not run inside the calling kernel (DEFER): ds_wls_fixup_kernel solves the queued problems right after the step
+// kernel.  Keeping that loop (a 2.5 KB stack frame, 400 DFMA, a call) out of the fused kernel is worth 2.4 % on the
+// mixed swarm and 9 % on the hexa-only workload even though it never executes there (profiles/r01_notes.md).
+struct WlsQueue {
+  int* count;    // entries queued by this launch
+  int* index;    // [n] vehicle ids
+  float* nu;     // [n][6] virtual controls of the queued vehicles (indexed by vehicle id)
+  int vehicle;   // this lane's vehicle id, < 0: the lane must not queue (tile padding)
+};
+
+template <bool NU6, bool EXT, bool DEFER = false>
 __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWlsDev* __restrict__ wls_tab, int type_id,
                                                 const CtrlState& s, const CtrlTarget& t, float inv_dt, float acc_b, CtrlMem& m,
-                                                CtrlOut& o, bool want_yaw_err) {
+                                                CtrlOut& o, bool want_yaw_err, const WlsQueue* wq = nullptr) {
   // ---- position loop (INDIControl.py:278-296 / INDIControl_6DOF.py:390-413)
   o.pex = t.x - s.px; o.pey = t.y - s.py; o.pez = t.z - s.pz;
   float asx = (o.pex * tp.kp + t.vx - s.vx) * tp.kd;
@@ -162,7 +173,20 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
         feasible = feasible && !(du[i] >= umax + 1.0f || du[i] <= umin - 1.0f);  // wls_alloc.py:264
       }
       o.wls_iter = 1;
-      if (!feasible) {  // rare: run the active-set iterations in FP64
+      if (DEFER) {
+        if (!feasible) {  // rare: hold the command now, ds_wls_fixup_kernel applies the active-set solution
+          o.wls_iter = 2;
+          if (wq->vehicle >= 0) {
+            const int qi = atomicAdd(wq->count, 1);
+            wq->index[qi] = wq->vehicle;
+            float* dst = wq->nu + (size_t)wq->vehicle * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dst[i] = nu[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) du[i] = 0.f;
+        }
+      } else if (!feasible) {  // rare: run the active-set iterations in FP64
         const DsWlsDev* P = wls_tab + type_id;
         double v[6], umin[6], umax[6], u[6];
         for (int i = 0; i < 6; ++i) {

@@ -80,6 +80,10 @@ struct DsArgs {
   float4* s_r0;    // actual rotor speed 0..3 (first-order motor model)
   float2* s_r1;    // actual rotor speed 4..5
   float4* s_af;    // filtered angular-acceleration estimate x y z | -
+  // deferred WLS slow path: problems queued by the fused kernel for ds_wls_fixup_kernel (6-DOF types only)
+  int* wls_count;  // this launch's counter
+  int* wls_index;  // [n]
+  float* wls_nu;   // [n][6]
   const DsTypeDev* types;
   const DsWlsDev* wls;
   const uint8_t* slot_type;

@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
         ds_allocate_quad<NU6>(tp, nu, m, o);
       } else {
         CtrlTarget t = ds_fetch_target(a, tp, cs, vv, wp, tg0);
-        ds_indi_control<NU6, EXT>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, a.acc_b, m, o, false);
+        // the fused kernel never runs the FP64 active-set loop itself (order 1 with 6-DOF types is un-fused by the host)
+        const WlsQueue wq = {a.wls_count, a.wls_index, a.wls_nu, valid ? v : -1};
+        ds_indi_control<NU6, EXT, true>(tp, a.wls, type_id, cs, t, a.inv_ctrl_dt, a.acc_b, m, o, false, &wq);
       }
       perr = sqrtf(o.pex * o.pex + o.pey * o.pey + o.pez * o.pez);
       lthrust = m.lthrust;

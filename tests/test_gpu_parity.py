@@ -780,3 +780,49 @@ def test_max_drones_per_env_downwash():
     exp = orc.adjacency_bits()
     assert (got == exp).mean() > 0.99 and ((got >> np.arange(D, dtype=np.uint32)) & 1).all()  # 32-bit rows, self bit set
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# the WLS slow path inside the fused step: lanes whose first iterate leaves the +-1.0 slack (wls_alloc.py:264) are
+# queued and solved by ds_wls_fixup_kernel right after the step kernel - against the oracle's full wls_alloc
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [0, 1])
+def test_wls_slow_path_in_the_fused_step(order):
+    _need_gpu()
+    from dronesim_b200 import _lib as L
+
+    models = ["hexa_6DOF", "robobee"]
+    E, K = 48, 2
+    core, orc = make_pair(models, E, "quat", K=K, stats=True)
+    rng = np.random.default_rng(51)
+    pos0 = np.zeros((E, 2, 3)) + [[0.0, 0.0, 2.0], [2.0, 0.0, 2.0]]
+    core.reset(pos0, action0=np.zeros((E, 2, 6)))  # first physics step with the all-zero action, like the oracle loop below
+    orc.reset(pos0)
+    # violent tumbling: the rate loop asks for far more than the rotors can give -> infeasible first iterate
+    w0 = rng.normal(0, 25.0, (E, 2, 3))
+    w0[::3] *= 0.01  # a third of the envs stay on the closed-form path
+    core.views()["omega_body"][:] = torch.tensor(w0.reshape(-1, 3), dtype=torch.float32, device="cuda")
+    orc.rates[:] = w0
+    tpos = pos0 + rng.uniform(-0.5, 0.5, pos0.shape)
+    tgt = core.targets_per_vehicle(np.concatenate([tpos.reshape(-1, 3), np.zeros((2 * E, 1))], axis=1))
+    act = np.zeros((E, 2, 6))
+    n_slow = 0
+    for step in range(3):
+        core.step(tgt, 1, order=order)
+        if order == 0:
+            orc.physics_step(act)
+            act = orc.control_step(tpos)
+        else:
+            act = orc.control_step(tpos)
+            orc.physics_step(act)
+        n_slow += sum(orc.ctrl[e][0].last_wls_iter != 1 for e in range(E))
+        got = core.cmd().cpu().numpy().reshape(E, 2, 6)
+        np.testing.assert_allclose(got[:, 0, :], act[:, 0, :], atol=5e-5, err_msg="hexa cmd, step %d" % step)
+        np.testing.assert_allclose(got[:, 1, :4], act[:, 1, :4], atol=5e-5, err_msg="quad cmd, step %d" % step)
+    assert n_slow >= 10  # the scenario does exercise the active-set iterations
+    st = core.stats()
+    if order == 0:  # the fused kernel counts what it defers; the un-fused order-1 path runs the in-line solver
+        assert st["wls_slow_path"] == n_slow
+    assert st["wls_non_converged"] == sum(orc.ctrl[e][0].wls_fail for e in range(E))
+    _compare_state(core, orc, pos_tol=2e-4, att_tol=2e-3, vel_tol=2e-2, what="tumbling hexa")
+    core.close()

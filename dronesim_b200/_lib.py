@@ -116,7 +116,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # translation units: the C ABI + small kernels, and the step kernel's instantiations split by (integrator, mode, rotors)
 _UNITS = [("ds_api.cu", "api", [])] + [
     ("ds_step_inst.cu", "step_%s%d_%d" % ("qr"[i], m, n), ["-DDS_INST_INTEG=%d" % i, "-DDS_INST_MODE=%d" % m, "-DDS_INST_NU6=%d" % n])
-    for i in (0, 1) for m in (0, 1) for n in (0, 1)]
+    for i in (0, 1) for m in (0, 1, 2) for n in (0, 1)]
 
 
 def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: str = None, only_units=None) -> str:
@@ -142,7 +142,7 @@ def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: 
         return obj, subprocess.run(cmd, capture_output=True, text=True)
 
     units = [u for u in _UNITS if only_units is None or u[1] in only_units]
-    with ThreadPoolExecutor(max_workers=len(units)) as ex:
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
         results = list(ex.map(compile_unit, units))
     for obj, res in results:
         if res.returncode != 0:

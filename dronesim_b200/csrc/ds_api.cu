@@ -414,13 +414,12 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
 
 // The step-kernel instantiations live in ds_step_inst.cu, compiled once per (integrator, mode) pair so that the
 // translation units build in parallel; see ds_step_inst.cuh for the dispatcher.
-template <int MODE>
-static void launch_step(const ds_handle* h, const DsArgs& a, cudaStream_t st) {
+static void launch_step(int mode, const ds_handle* h, const DsArgs& a, cudaStream_t st) {
   // downwash variant: 0 off, 1 every ordered pair, 2 symmetric pairs (16 drones per env, one Gaussian width for all types)
   int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
   if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;
   const int grid = grid_for(h, a.n_tiles, DS_MIN_CTAS);
-  ds_launch_step(h->cfg.integrator == DS_INTEG_RPY ? 1 : 0, MODE, dw, h->nu6, 32 % a.D == 0, a, grid, st);
+  ds_launch_step(h->cfg.integrator == DS_INTEG_RPY ? 1 : 0, mode, dw, h->nu6, 32 % a.D == 0, a, grid, st);
 }
 
 static int log_sample(ds_handle* h, cudaStream_t st);
@@ -467,7 +466,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
     a.wls_count = h->d_wls_count ? h->d_wls_count + h->wls_phase : nullptr;
     a.wls_index = h->d_wls_index; a.wls_nu = h->d_wls_nu;
     time_flags(h, a);
-    launch_step<0>(h, a, st);
+    launch_step(order == DS_ORDER_CONTROL_THEN_PHYSICS ? 2 : 0, h, a, st);
     h->launches++;
     if (h->any_6dof) {  // solve what the step kernel queued; re-arm the other counter for the next step
       ds_wls_fixup_kernel<<<grid_for(h, 1 << 20, 1), 128, 0, st>>>(a, h->d_wls_count + (h->wls_phase ^ 1));
@@ -492,7 +491,7 @@ extern "C" int ds_physics_step(ds_handle* h, const float* action, void* stream) 
   a.ext_action = action;
   a.store_act = 1;
   time_flags(h, a);
-  launch_step<1>(h, a, (cudaStream_t)stream);
+  launch_step(1, h, a, (cudaStream_t)stream);
   h->launches++;
   CK(cudaGetLastError());
   h->first_action_pending = false;

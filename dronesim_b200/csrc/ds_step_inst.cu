@@ -1,11 +1,11 @@
 // Instantiations of ds_step_kernel for ONE (integrator, mode, rotor-count) triple: compile with
-//   -DDS_INST_INTEG=0|1 (QUAT | RPY)  -DDS_INST_MODE=0|1 (fused dynamics + INDI | physics only)
+//   -DDS_INST_INTEG=0|1 (QUAT | RPY)  -DDS_INST_MODE=0|1|2 (fused physics-then-control | physics only | fused control-then-physics)
 //   -DDS_INST_NU6=0|1 (all types have <= 4 rotors | some type has 6).
 #include "ds_kernels.cuh"
 #include "ds_step_inst.cuh"
 
 #ifndef DS_INST_INTEG
-#error "compile ds_step_inst.cu with -DDS_INST_INTEG=0|1 -DDS_INST_MODE=0|1 -DDS_INST_NU6=0|1"
+#error "compile ds_step_inst.cu with -DDS_INST_INTEG=0|1 -DDS_INST_MODE=0|1|2 -DDS_INST_NU6=0|1"
 #endif
 
 // two tile stages of dynamic shared memory (> 48 KB: opt in once per instantiation and device)

@@ -9,7 +9,7 @@ Workload (``config.workload``): BASELINE.json configs[4] "scaling sweep 1M-64M v
 substeps/control step" at 4 Mi vehicles PER GPU (262144 envs x 16 drones; weak scaling), each env
 being configs[3]'s heterogeneous swarm: 8 quads (robobee / tello) + 8 hexa_6DOF, ground effect +
 drag + downwash, K = 8 physics substeps per INDI evaluation, hover targets, noise off, quaternion
-integrator.  4 Mi vehicles = 461 MB of resident state per GPU, > 3.6x the 126 MB L2, so every step
+integrator.  4 Mi vehicles = 503 MB of resident state per GPU, 4x the 126 MB L2, so every step
 streams its state from HBM (no L2 flush needed between steps; said in ``config.l2``).
 
 One "step" = one control step = ONE launch of the fused kernel over the whole shard
@@ -74,7 +74,7 @@ def workload_config(envs_per_gpu: int, n_gpus: int) -> dict:
         "substeps_per_control_step": K_SUBSTEPS,
         "sim_freq_hz": 240,
         "parallelism": "envs sharded over %d GPU(s), no per-step collective" % n_gpus,
-        "l2": "inputs larger than L2 (resident state %.0f MB per GPU vs 126 MB L2); no flush" % (envs_per_gpu * DRONES * 110 / 1e6),
+        "l2": "inputs larger than L2 (resident state %.0f MB per GPU vs 126 MB L2); no flush" % (envs_per_gpu * DRONES * 120 / 1e6),
     }
 
 

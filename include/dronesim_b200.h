@@ -191,7 +191,11 @@ int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, const float* ve
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* n_control_steps x { K physics substeps with the held command ; one INDI evaluation } fused in
- * one kernel per control step: examples/fly_INDI.py:217-245 for all vehicles at once. */
+ * one kernel per control step: examples/fly_INDI.py:217-245 for all vehicles at once.  `order` picks the kernel
+ * variant (DS_ORDER_*).  When a 6-DOF type is present every step kernel is followed by a tiny fix-up kernel that
+ * solves the WLS allocation of the (rare) vehicles whose closed-form first iterate was infeasible
+ * (wls_alloc.py:264) - the command they apply in the NEXT physics step; with DS_ORDER_CONTROL_THEN_PHYSICS and a
+ * 6-DOF type the step runs as a control kernel followed by a physics kernel instead (same results). */
 int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_steps, int32_t order, void* stream);
 /* BaseAviary.step with an external action (BaseAviary.py:428-555): clip (CtrlAviary.py:258-263),
  * K substeps.  action: DEVICE [N][DS_MAX_ROTORS] PWM. */

@@ -1,6 +1,6 @@
 // Host-side dispatcher of the ds_step_kernel instantiations.
 //
-// ds_step_kernel<INTEG, DW, NU6, WARPSYNC, MODE, FX> has ~50 useful instantiations of a ~9000-instruction kernel;
+// ds_step_kernel<INTEG, DW, NU6, WARPSYNC, MODE, FX, EXT> has ~150 instantiations of a 2,600-instruction kernel;
 // they are split over twelve translation units (ds_step_inst.cu compiled with -DDS_INST_INTEG=0|1 -DDS_INST_MODE=0|1|2
 // -DDS_INST_NU6=0|1)
 // that nvcc builds in parallel.  ds_api.cu only sees the declarations below.

@@ -826,3 +826,56 @@ def test_wls_slow_path_in_the_fused_step(order):
     assert st["wls_non_converged"] == sum(orc.ctrl[e][0].wls_fail for e in range(E))
     _compare_state(core, orc, pos_tol=2e-4, att_tol=2e-3, vel_tol=2e-2, what="tumbling hexa")
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# the libm-free controller (MUFU sin / cos, polynomial atan2) over the whole attitude range, incl. the gimbal branch
+# (|sin pitch| >= 0.99999, oracle/pyb_math.py) and yaw errors beyond +-pi (norm_ang), against the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["robobee", "tello", "hexa_6DOF"])
+def test_controller_over_the_whole_attitude_range(name):
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.vehicles import load_vehicle
+    from oracle import control as oc
+    from oracle import pyb_math as pm
+
+    vt = load_vehicle(name)
+    n_u = vt.INDI_ACTUATOR_NR
+    n = 1500
+    rng = np.random.default_rng(61)
+    rpy = np.stack([rng.uniform(-3.1, 3.1, n), rng.uniform(-1.55, 1.55, n), rng.uniform(-3.1, 3.1, n)], axis=1)
+    rpy[:40, 1] = np.pi / 2 * np.sign(rng.normal(size=40))          # exactly on the gimbal branch
+    rpy[40:80, 1] = (np.pi / 2 - 1e-3) * np.sign(rng.normal(size=40))  # just inside it (sin > 0.99999)
+    rpy[80:120, 0] = 0.0
+    rpy[80:120, 1] = 0.0                                             # level: roll / pitch atan2(0, 1)
+    states = np.zeros((n, 22))
+    states[:, 0:3] = rng.uniform(-2, 2, (n, 3))
+    states[:, 3:7] = [pm.getQuaternionFromEuler(a) for a in rpy]
+    states[:, 10:13] = rng.normal(0, 0.5, (n, 3))
+    states[:, 13:16] = rng.normal(0, 0.5, (n, 3))
+    tpos = states[:, 0:3] + rng.normal(0, 0.3, (n, 3))
+    tyaw = rng.uniform(-6.0, 6.0, n)                                 # far beyond +-pi
+    core = SwarmCore([name], n)
+    core.reset(np.zeros((n, 3)))
+    tgt = core.targets_per_vehicle(np.concatenate([tpos, tyaw[:, None]], axis=1))
+    cmd, pe, ye = core.control_from_state(torch.tensor(states, dtype=torch.float32, device="cuda"), tgt, 5 / 240)
+    cmd, pe, ye = cmd.cpu().numpy(), pe.cpu().numpy(), ye.cpu().numpy()
+    err = np.zeros(n)
+    for i in range(n):
+        c = oc.make_controller(vt)
+        ref_cmd, ref_pe, ref_ye = c.computeControlFromState(control_timestep=5 / 240, state=states[i, : 16 + n_u],
+                                                            target_pos=tpos[i], target_rpy=np.array([0.0, 0.0, tyaw[i]]))
+        err[i] = np.abs(cmd[i, :n_u] - ref_cmd).max()
+        np.testing.assert_allclose(pe[i], ref_pe, atol=1e-5)
+        if n_u == 4:
+            d = (ye[i] - ref_ye + np.pi) % (2 * np.pi) - np.pi
+            assert abs(d) <= 2e-5, (i, ye[i], ref_ye)
+    # Validity envelope of FP32 (measured identically with libm trig): the quad law divides by T cos(roll)
+    # (INDIControl.py:319-339, G is singular at roll = +-pi/2), so within |cos(roll)| < 0.05 the command error grows
+    # like eps / cos(roll)^2; everywhere else - gimbal branch included - the 2e-5 PWM bound of the fixtures holds.
+    regular = np.abs(np.cos(rpy[:, 0])) >= 0.05 if n_u == 4 else np.ones(n, bool)
+    assert regular.sum() > 0.9 * n
+    assert err[regular].max() <= 2e-5, (err[regular].max(), rpy[regular][err[regular].argmax()])
+    assert np.isfinite(cmd).all() and err.max() <= 2e-2
+    core.close()

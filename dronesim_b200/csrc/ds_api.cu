@@ -38,6 +38,8 @@ struct ds_handle {
   int* d_wls_index = nullptr;   // [n]
   float* d_wls_nu = nullptr;    // [n][6]
   int wls_phase = 0;
+  int* d_tile_counter = nullptr;  // [2] dynamic tile scheduler counters, alternating per launch
+  int tile_phase = 0;
   float* d_cmd_scratch = nullptr;  // [n][6]: un-fused control -> physics hand-over (order 1 with 6-DOF types)
   DsTypeDev* d_types = nullptr;
   DsWlsDev* d_wls = nullptr;
@@ -91,7 +93,7 @@ static void free_all(ds_handle* h) {
                   h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
                   h->d_roll_done[1], h->d_log_ids, h->d_log_states, h->s_r0, h->s_r1, h->s_af, h->d_wls_count, h->d_wls_index, h->d_wls_nu,
-                  h->d_cmd_scratch};
+                  h->d_cmd_scratch, h->d_tile_counter};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; ++b) {
@@ -147,6 +149,7 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   alloc((void**)&h->d_init_cmd, sizeof(float) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_init_thrust, sizeof(float) * DS_MAX_TYPES_DEV);
   alloc((void**)&h->d_stats, sizeof(double) * DS_NUM_STATS);
+  alloc((void**)&h->d_tile_counter, 2 * sizeof(int));
   if (e != cudaSuccess) {
     free_all(h);
     delete h;
@@ -414,7 +417,10 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
 
 // The step-kernel instantiations live in ds_step_inst.cu, compiled once per (integrator, mode) pair so that the
 // translation units build in parallel; see ds_step_inst.cuh for the dispatcher.
-static void launch_step(int mode, const ds_handle* h, const DsArgs& a, cudaStream_t st) {
+static void launch_step(int mode, ds_handle* h, DsArgs& a, cudaStream_t st) {
+  a.tile_counter = h->d_tile_counter + h->tile_phase;
+  a.tile_counter_next = h->d_tile_counter + (h->tile_phase ^ 1);
+  h->tile_phase ^= 1;
   // downwash variant: 0 off, 1 every ordered pair, 2 symmetric pairs (16 drones per env, one Gaussian width for all types)
   int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
   if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;

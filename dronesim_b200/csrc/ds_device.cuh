@@ -84,6 +84,10 @@ struct DsArgs {
   int* wls_count;  // this launch's counter
   int* wls_index;  // [n]
   float* wls_nu;   // [n][6]
+  // dynamic tile scheduler: tiles beyond the first two of each CTA are handed out by an atomic counter; the launch
+  // zeroes the counter the NEXT launch will use (two counters alternate, so no memset between launches)
+  int* tile_counter;
+  int* tile_counter_next;
   const DsTypeDev* types;
   const DsWlsDev* wls;
   const uint8_t* slot_type;

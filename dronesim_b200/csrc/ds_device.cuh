@@ -8,11 +8,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// 128 vehicles per tile x 4 resident CTAs per SM (16 warps, 128 registers per thread): with the dynamic tile tickets the
+// smaller tile halves the tail of a launch; measured 1-5 % faster than 256 x 2 on every workload (profiles/r01_notes.md)
 #ifndef DS_TILE
-#define DS_TILE 256          // threads per CTA = vehicles per tile (when drones_per_env divides it)
+#define DS_TILE 128          // threads per CTA = vehicles per tile (when drones_per_env divides it)
 #endif
 #ifndef DS_MIN_CTAS
-#define DS_MIN_CTAS 2        // resident CTAs per SM the step kernel is compiled for (register budget)
+#define DS_MIN_CTAS 4        // resident CTAs per SM the step kernel is compiled for (register budget)
 #endif
 #define DS_MAX_TYPES_DEV 8
 #define DS_DW_ROWS (DS_TILE + DS_TILE / 2)       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2

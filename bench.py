@@ -195,7 +195,7 @@ def run_reference(args):
                 "the reference's own implementation of this path is not runnable (dead DYN code, PyBullet absent)"
                 % (args.steps, args.warmup, steps, warm),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -447,12 +447,24 @@ def run_ours(args):
             "control_steps_per_s": N * n_gpus * args.steps / (ms_total * 1e-3),
             "rollout_stats": stats, "sane": bool(sane), "other_workloads": others,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0 if sane else 3
 
 
+def _emit(line: dict):
+    """The ONE JSON line, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse_args()
+    # Native libraries print to fd 1 behind Python's back (NCCL's version banner under torchrun): keep the real stdout for
+    # the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -68,15 +68,8 @@ __device__ __forceinline__ void ds_downwash_pair(float& acc, const float4 o, flo
                                                  float k3) {
   const float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
   const float d2 = fmaf(dy, dy, dx * dx);
-#ifdef DS_EXP_PAIR2  // experiment: 2 MUFU + 3 more FMUL/FADD per pair
-  const float bt = fmaf(k2, dz, k3) + 1e-30f;
-  const float t = ds_rcp(dz * bt);
-  const float idz = t * bt, ib = t * dz;
-  const float idz2 = idz * idz;
-#else
   const float ib = ds_rcp(fmaf(k2, dz, k3));   // 1 / beta'
   const float idz2 = ds_rcp(dz * dz);          // 1 / dz^2
-#endif
   const float w = idz2 * ds_ex2((ib * ib) * -d2);
   asm("{\n\t.reg .pred p;\n\t"
       "setp.gt.f32 p, %1, 0f00000000;\n\t"

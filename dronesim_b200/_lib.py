@@ -92,6 +92,7 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p]),
     "ds_rate_control_step": (C.c_int, [_H, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "ds_get_obs": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_set_env_outputs": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ds_views": (C.c_int, [_H, C.POINTER(ds_state_views)]),
     "ds_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
     "ds_stats_reset": (C.c_int, [_H, C.c_void_p]),

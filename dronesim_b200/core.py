@@ -291,6 +291,14 @@ class SwarmCore:
         L.check(L.lib().ds_get_obs(self._h, self._p(obs), self._p(nb), self._p(dn), self._p(rw), self._stream()), self._h)
         return obs, nb, dn, rw
 
+    def set_env_outputs(self, done: bool = True, reward: bool = True):
+        """Arm per-env ``done [E] uint8`` / ``reward [E] float32`` device tensors that every following ``step`` fills
+        (inside the fused kernel, by warp shuffles, when drones_per_env divides 32).  Returns the two tensors."""
+        self._env_done = torch.zeros((self.E,), dtype=torch.uint8, device=self.device) if done else None
+        self._env_reward = torch.zeros((self.E,), dtype=torch.float32, device=self.device) if reward else None
+        L.check(L.lib().ds_set_env_outputs(self._h, self._p(self._env_done), self._p(self._env_reward)), self._h)
+        return self._env_done, self._env_reward
+
     def step_host(self, host_pos_yaw: torch.Tensor, host_obs: Optional[torch.Tensor], host_done: Optional[torch.Tensor]):
         """End-to-end control step with HOST (ideally pinned) buffers; synchronises."""
         L.check(L.lib().ds_step_host(self._h, C.c_void_p(host_pos_yaw.data_ptr()),

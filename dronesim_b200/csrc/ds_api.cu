@@ -40,6 +40,8 @@ struct ds_handle {
   int wls_phase = 0;
   int* d_tile_counter = nullptr;  // [2] dynamic tile scheduler counters, alternating per launch
   int tile_phase = 0;
+  uint8_t* env_done_out = nullptr;  // ds_set_env_outputs
+  float* env_reward_out = nullptr;
   float* d_cmd_scratch = nullptr;  // [n][6]: un-fused control -> physics hand-over (order 1 with 6-DOF types)
   DsTypeDev* d_types = nullptr;
   DsWlsDev* d_wls = nullptr;
@@ -373,6 +375,7 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.n = h->n; a.D = h->cfg.drones_per_env; a.tile_v = h->tile_v; a.n_tiles = h->n_tiles;
   a.K = h->cfg.substeps; a.n_types = h->n_types;
   a.rc_kind = h->rc_kind;
+  a.reward_mode = h->cfg.reward_mode;
   a.s_r0 = h->s_r0; a.s_r1 = h->s_r1; a.s_af = h->s_af;
   a.ext = h->ext ? 1 : 0;
   a.motor_a = h->cfg.motor_tau > 0.f ? (float)(1.0 - exp(-(1.0 / (double)h->cfg.sim_freq) / (double)h->cfg.motor_tau)) : 2.0f;
@@ -462,6 +465,10 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
       rc = ds_physics_step(h, h->d_cmd_scratch, stream);
       if (rc != DS_OK) return rc;
       h->act_valid = false;  // obs tail = the controller command (which is the action just applied)
+      if (h->env_done_out || h->env_reward_out) {
+        rc = ds_get_obs(h, nullptr, nullptr, h->env_done_out, h->env_reward_out, stream);
+        if (rc != DS_OK) return rc;
+      }
     }
     return DS_OK;
   }
@@ -471,6 +478,9 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
     a.store_act = 0;
     a.wls_count = h->d_wls_count ? h->d_wls_count + h->wls_phase : nullptr;
     a.wls_index = h->d_wls_index; a.wls_nu = h->d_wls_nu;
+    const bool env_in_kernel = (32 % h->cfg.drones_per_env) == 0;  // every env inside one warp: shuffle reduction
+    a.env_done = env_in_kernel ? h->env_done_out : nullptr;
+    a.env_reward = env_in_kernel ? h->env_reward_out : nullptr;
     time_flags(h, a);
     launch_step(order == DS_ORDER_CONTROL_THEN_PHYSICS ? 2 : 0, h, a, st);
     h->launches++;
@@ -483,8 +493,19 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
     h->act_valid = false;
     h->step_counter += h->cfg.substeps;  // BaseAviary.py:554
     log_sample(h, st);
+    if (!env_in_kernel && (h->env_done_out || h->env_reward_out)) {
+      rc = ds_get_obs(h, nullptr, nullptr, h->env_done_out, h->env_reward_out, stream);
+      if (rc != DS_OK) return rc;
+    }
   }
   CK(cudaGetLastError());
+  return DS_OK;
+}
+
+extern "C" int ds_set_env_outputs(ds_handle* h, uint8_t* done_env, float* reward_env) {
+  if (!h) return DS_ERR_INVALID;
+  h->env_done_out = done_env;
+  h->env_reward_out = reward_env;
   return DS_OK;
 }
 
@@ -715,13 +736,18 @@ extern "C" int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t 
     memset(&t, 0, sizeof(t));
     t.mode = 0;
     t.pos_yaw = (const float*)h->d_roll_tgt[b];
-    int rc = ds_step(h, &t, 1, DS_ORDER_PHYSICS_THEN_CONTROL, stream);
-    if (rc != DS_OK) return rc;
+    // the per-env done flags of step i are reduced inside the step kernel (warp shuffles) straight into buffer b
+    uint8_t* const saved_done = h->env_done_out;
+    float* const saved_reward = h->env_reward_out;
     if (host_done_env) {
       if (i >= 2) CK(cudaStreamWaitEvent(st, h->ev_drained[b], 0));  // done buffer b has left for the host
-      rc = ds_get_obs(h, nullptr, nullptr, h->d_roll_done[b], nullptr, stream);
-      if (rc != DS_OK) return rc;
+      h->env_done_out = h->d_roll_done[b];
+      h->env_reward_out = nullptr;
     }
+    int rc = ds_step(h, &t, 1, DS_ORDER_PHYSICS_THEN_CONTROL, stream);
+    h->env_done_out = saved_done;
+    h->env_reward_out = saved_reward;
+    if (rc != DS_OK) return rc;
     CK(cudaEventRecord(h->ev_computed[b], st));
     if (host_done_env) {
       CK(cudaStreamWaitEvent(h->st_d2h, h->ev_computed[b], 0));

@@ -127,6 +127,11 @@ struct DsArgs {
   int goal_en, floor_en, time_hit;
   float goal_x, goal_y, goal_z, goal_r;
   float z_min;
+  // per-env outputs of the fused step (optional, DEVICE): reduced with warp shuffles inside the step kernel when every env
+  // sits inside one warp (D | 32); the host falls back to the observation kernel otherwise
+  uint8_t* env_done;   // [n_envs]
+  float* env_reward;   // [n_envs]
+  int reward_mode;
   // external I/O of the non-fused entry points
   const float* ext_action;   // [n][6]
   const float* ext_state;    // [n][22]

@@ -331,6 +331,23 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
     if (a.floor_en && s.pz < a.z_min) done_bits |= 2u;
     if (a.time_hit) done_bits |= 4u;
 
+    // ---- per-env done / reward (CtrlAviary._computeDone / _computeReward, CtrlAviary.py:267-293, batched): a butterfly of
+    // warp shuffles over the D lanes of the env, the env's slot 0 writes.  Same rule as ds_obs_kernel: the goal bit counts
+    // for slot 0 only (the example tests drone "0"), floor / time for every slot.
+    if (WARPSYNC && MODE != 1 && (a.env_done != nullptr || a.env_reward != nullptr)) {
+      uint32_t db = valid ? ((slot == 0) ? done_bits : (done_bits & 6u)) : 0u;
+      float pe = valid ? perr : 0.f;
+      for (int o = a.D >> 1; o > 0; o >>= 1) {
+        db |= __shfl_xor_sync(0xffffffffu, db, o);
+        pe += __shfl_xor_sync(0xffffffffu, pe, o);
+      }
+      if (valid && slot == 0) {
+        const int env = v / a.D;
+        if (a.env_done) a.env_done[env] = db ? 1 : 0;
+        if (a.env_reward) a.env_reward[env] = (a.reward_mode == 1) ? -pe / (float)a.D : -1.0f;
+      }
+    }
+
     if (valid) {
       a.s_pos[v] = make_float4(s.px, s.py, s.pz, lthrust);
       a.s_quat[v] = make_float4(s.qx, s.qy, s.qz, s.qw);

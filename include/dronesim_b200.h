@@ -221,6 +221,11 @@ int ds_rate_control_step(ds_handle* h, const float* rate_thrust, float control_t
  * done_env DEVICE [n_envs] uint8; reward_env DEVICE [n_envs] float (constant -1, CtrlAviary.py:267-278).
  * Any pointer may be NULL. */
 int ds_get_obs(ds_handle* h, float* obs, uint32_t* neighbors, uint8_t* done_env, float* reward_env, void* stream);
+/* Arms per-env outputs of every following ds_step: done_env DEVICE [n_envs] uint8 and / or reward_env DEVICE [n_envs]
+ * float (NULL, NULL disarms), written with the values ds_get_obs would return after that step.  When every env sits
+ * inside one warp (drones_per_env divides 32) they are reduced with warp shuffles inside the fused kernel - no extra
+ * launch; otherwise ds_step launches the observation kernel for them. */
+int ds_set_env_outputs(ds_handle* h, uint8_t* done_env, float* reward_env);
 int ds_views(ds_handle* h, ds_state_views* out);
 /* Rollout statistics accumulated when DS_FLAG_STATS is set; synchronises the stream.
  * out[0]=control evaluations, [1]=sum |pos_e|^2, [2]=saturated rotor commands, [3]=WLS slow-path entries,

@@ -879,3 +879,36 @@ def test_controller_over_the_whole_attitude_range(name):
     assert err[regular].max() <= 2e-5, (err[regular].max(), rpy[regular][err[regular].argmax()])
     assert np.isfinite(cmd).all() and err.max() <= 2e-2
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# per-env done / reward produced by the fused step itself (warp-shuffle reduction when D | 32, observation kernel
+# otherwise) == what ds_get_obs reports after the step
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [16, 3, 1])
+def test_env_outputs_of_the_fused_step(D):
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    models = (["robobee", "hexa_6DOF", "tello"] * 6)[:D]
+    E, K = 37, 4
+    rng = np.random.default_rng(71)
+    pos0 = np.zeros((E, D, 3))
+    pos0[..., 0] = 1.5 * np.arange(D)[None, :]
+    pos0[..., 2] = 2.0 + rng.uniform(-0.05, 0.05, (E, 1)) + rng.uniform(-0.002, 0.002, (E, D))  # env-wide altitude offset
+    core = SwarmCore(models, E, aggregate_phy_steps=K, ground=True, drag=True, downwash=D > 1, z_min=1.99, goal=[0.0, 0.0, 2.0],
+                     goal_radius=0.03, reward_mode=1)
+    core.reset(pos0)
+    done, reward = core.set_env_outputs()
+    tgt = core.targets_per_vehicle(np.concatenate([pos0.reshape(-1, 3) + rng.uniform(-0.3, 0.3, (E * D, 3)),
+                                                   np.zeros((E * D, 1))], axis=1))
+    first = None
+    for step in range(6):
+        core.step(tgt, 1)
+        _, _, dn, rw = core.get_obs(state=False, neighbors=False, done=True, reward=True)
+        np.testing.assert_array_equal(done.cpu().numpy(), dn.cpu().numpy())
+        np.testing.assert_allclose(reward.cpu().numpy(), rw.cpu().numpy(), rtol=1e-6, atol=1e-7)
+        first = dn.cpu().numpy().copy() if first is None else first
+    # envs that start below the floor (or with slot 0 inside the goal sphere) are done after the first step, the others not yet
+    assert first.any() and not first.all() and (reward.cpu().numpy() < 0).all()
+    core.close()

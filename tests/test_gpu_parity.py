@@ -912,3 +912,55 @@ def test_env_outputs_of_the_fused_step(D):
     # envs that start below the floor (or with slot 0 inside the goal sphere) are done after the first step, the others not yet
     assert first.any() and not first.all() and (reward.cpu().numpy() < 0).all()
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# long rollouts: 10 s of closed loop against the oracle (quaternion norm, controller memory and integrator stay in
+# step over 2,400 substeps), and the qualitative hover behaviour the reference examples show - a swarm started off its
+# set-points settles onto them.  (At 30 Hz control - K = 8 - the reference's 6-DOF law is only marginally stable: the
+# FP64 oracle drifts off the set-point after ~40 s exactly as the CUDA core does; at the 96 Hz the reference example
+# uses - K = 2 - it holds the hover indefinitely.)
+# ------------------------------------------------------------------------------------------
+def test_ten_seconds_closed_loop_vs_oracle():
+    _need_gpu()
+    models = ["robobee", "hexa_6DOF"]
+    E, K = 1, 8
+    core, orc = make_pair(models, E, "quat", K=K, gnd=True, drag=True)
+    pos0 = np.array([[[0.0, 0.0, 3.0], [2.0, 0.0, 3.0]]])
+    act0 = np.zeros((E, 2, 6))
+    act0[:, 0, :4] = 0.45
+    act0[:, 1, :] = 0.45
+    core.reset(pos0, action0=act0)
+    orc.reset(pos0)
+    tgt = core.targets_per_vehicle(np.concatenate([pos0.reshape(-1, 3), np.zeros((2, 1))], axis=1))
+    act = act0.copy()
+    for step in range(300):
+        core.step(tgt, 1)
+        orc.physics_step(act)
+        act = orc.control_step(pos0)
+    _compare_state(core, orc, pos_tol=3e-4, att_tol=3e-4, vel_tol=2e-3, what="10 s closed loop")
+    st = core_state(core)
+    assert np.abs(np.linalg.norm(st["quat"], axis=1) - 1.0).max() < 1e-6
+    assert np.linalg.norm(st["pos"] - pos0.reshape(-1, 3), axis=1).max() < 2e-3  # both have settled on their set-points
+    core.close()
+
+
+def test_hover_settles_and_holds_at_the_reference_control_rate():
+    """fly_hexa_6DOF.py / fly_INDI.py rates: 240 Hz physics, 96 Hz control (K = 2), 30 s, 64 envs of quad + hexa started
+    0.3 m off their set-points with ground effect + drag + downwash."""
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    E = 64
+    rng = np.random.default_rng(81)
+    tpos = np.zeros((E, 2, 3)) + [[0.0, 0.0, 2.0], [1.5, 0.0, 2.6]]
+    pos0 = tpos + rng.uniform(-0.3, 0.3, tpos.shape)
+    core = SwarmCore(["tello", "hexa_6DOF"], E, aggregate_phy_steps=2, ground=True, drag=True, downwash=True, stats=True)
+    core.reset(pos0)
+    tgt = core.targets_per_vehicle(np.concatenate([tpos.reshape(-1, 3), np.zeros((2 * E, 1))], axis=1))
+    core.step(tgt, 30 * 120)
+    st = core_state(core)
+    err = np.linalg.norm(st["pos"] - tpos.reshape(-1, 3), axis=1)
+    assert err.max() < 1e-3, err.max()
+    assert np.abs(st["vel"]).max() < 1e-3 and core.stats()["non_finite"] == 0
+    core.close()

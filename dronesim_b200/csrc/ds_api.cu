@@ -34,12 +34,10 @@ struct ds_handle {
   float4 *s_r0 = nullptr, *s_af = nullptr;  // extension state: rotor speeds, filtered angular acceleration
   float2* s_r1 = nullptr;
   bool ext = false;
-  int* d_wls_count = nullptr;   // [2] alternating per step (the fix-up kernel of step i re-arms the counter of step i + 1)
+  int* d_wls_count = nullptr;   // [2]: queue length, exit counter of the fix-up kernel (which re-arms both)
   int* d_wls_index = nullptr;   // [n]
   float* d_wls_nu = nullptr;    // [n][6]
-  int wls_phase = 0;
-  int* d_tile_counter = nullptr;  // [2] dynamic tile scheduler counters, alternating per launch
-  int tile_phase = 0;
+  int* d_tile_counter = nullptr;  // [2]: ticket counter, exit counter of the step kernel (whose last CTA re-arms both)
   uint8_t* env_done_out = nullptr;  // ds_set_env_outputs
   float* env_reward_out = nullptr;
   float* d_cmd_scratch = nullptr;  // [n][6]: un-fused control -> physics hand-over (order 1 with 6-DOF types)
@@ -421,9 +419,8 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
 // The step-kernel instantiations live in ds_step_inst.cu, compiled once per (integrator, mode) pair so that the
 // translation units build in parallel; see ds_step_inst.cuh for the dispatcher.
 static void launch_step(int mode, ds_handle* h, DsArgs& a, cudaStream_t st) {
-  a.tile_counter = h->d_tile_counter + h->tile_phase;
-  a.tile_counter_next = h->d_tile_counter + (h->tile_phase ^ 1);
-  h->tile_phase ^= 1;
+  a.tile_counter = h->d_tile_counter;
+  a.tile_done = h->d_tile_counter + 1;
   // downwash variant: 0 off, 1 every ordered pair, 2 symmetric pairs (16 drones per env, one Gaussian width for all types)
   int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
   if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;
@@ -476,7 +473,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
     a.use_act = (h->first_action_pending && order == 0) ? 1 : 0;
     a.step0 = (uint32_t)h->step_counter;  // substep index of k = 0 (noise stream counter)
     a.store_act = 0;
-    a.wls_count = h->d_wls_count ? h->d_wls_count + h->wls_phase : nullptr;
+    a.wls_count = h->d_wls_count;
     a.wls_index = h->d_wls_index; a.wls_nu = h->d_wls_nu;
     const bool env_in_kernel = (32 % h->cfg.drones_per_env) == 0;  // every env inside one warp: shuffle reduction
     a.env_done = env_in_kernel ? h->env_done_out : nullptr;
@@ -484,10 +481,9 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
     time_flags(h, a);
     launch_step(order == DS_ORDER_CONTROL_THEN_PHYSICS ? 2 : 0, h, a, st);
     h->launches++;
-    if (h->any_6dof) {  // solve what the step kernel queued; re-arm the other counter for the next step
-      ds_wls_fixup_kernel<<<grid_for(h, 1 << 20, 1), 128, 0, st>>>(a, h->d_wls_count + (h->wls_phase ^ 1));
+    if (h->any_6dof) {  // solve what the step kernel queued (and empty the queue for the next step)
+      ds_wls_fixup_kernel<<<grid_for(h, 1 << 20, 1), 128, 0, st>>>(a);
       h->launches++;
-      h->wls_phase ^= 1;
     }
     h->first_action_pending = false;
     h->act_valid = false;

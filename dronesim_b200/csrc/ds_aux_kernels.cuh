@@ -216,10 +216,9 @@ __global__ void __launch_bounds__(256) ds_reset_kernel(const DsResetArgs a) {
 // ---------------------------------------------------------------------------------------------
 // deferred WLS slow path: the problems the fused kernel queued (first iterate outside the +-1.0 slack, wls_alloc.py:264),
 // one per thread: FP64 active-set solution, cmd = clip(cmd + du) (INDIControl_6DOF.py:630-631); the fused kernel held
-// the command of these vehicles, and nothing reads it before the next step's physics.  Also re-arms the OTHER counter.
+// the command of these vehicles, and nothing reads it before the next step's physics.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ds_wls_fixup_kernel(const DsArgs a, int* next_count) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+__global__ void __launch_bounds__(128) ds_wls_fixup_kernel(const DsArgs a) {
   const int n = *a.wls_count;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
     const int v = a.wls_index[q];
@@ -249,6 +248,15 @@ __global__ void __launch_bounds__(128) ds_wls_fixup_kernel(const DsArgs a, int* 
     if (a.flags & 8u) {
       if (sat) atomicAdd(a.stats + ST_SAT, (double)sat);
       if (it < 0) atomicAdd(a.stats + ST_WLS_FAIL, 1.0);
+    }
+  }
+  // the last block out empties the queue for the next step kernel (every block has read the count by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.wls_count + 1, 1) == (int)gridDim.x - 1) {
+      a.wls_count[0] = 0;
+      a.wls_count[1] = 0;
     }
   }
 }

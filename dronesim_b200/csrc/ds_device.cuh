@@ -83,13 +83,13 @@ struct DsArgs {
   float2* s_r1;    // actual rotor speed 4..5
   float4* s_af;    // filtered angular-acceleration estimate x y z | -
   // deferred WLS slow path: problems queued by the fused kernel for ds_wls_fixup_kernel (6-DOF types only)
-  int* wls_count;  // this launch's counter
+  int* wls_count;  // entries queued by the step kernel; ds_wls_fixup_kernel re-arms it (and wls_count[1], its exit counter)
   int* wls_index;  // [n]
   float* wls_nu;   // [n][6]
-  // dynamic tile scheduler: tiles beyond the first two of each CTA are handed out by an atomic counter; the launch
-  // zeroes the counter the NEXT launch will use (two counters alternate, so no memset between launches)
+  // dynamic tile scheduler: tiles beyond the first two of each CTA are handed out by an atomic counter; the last CTA to
+  // leave the kernel re-arms it (no memset between launches, and a captured CUDA graph can be replayed as is)
   int* tile_counter;
-  int* tile_counter_next;
+  int* tile_done;
   const DsTypeDev* types;
   const DsWlsDev* wls;
   const uint8_t* slot_type;

@@ -200,7 +200,6 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
     // tile comes from the atomic counter, so that no SM idles while another still has a whole tile queued: -4.3 % on
     // the K = 8 mixed swarm (more than the 1.2 % of static imbalance: SMs do not run at the same pace), +2 % on the
     // K = 2 workloads whose tiles last 3 us; choosing static / dynamic per launch was measured and lost on both.
-    if (blockIdx.x == 0) *a.tile_counter_next = 0;
     sh_tile[0] = blockIdx.x;
     ds_stage_issue<NU6, MODE>(a, blockIdx.x, ds_stage_mem, &sh_bar[0]);
     const int t1 = blockIdx.x + gridDim.x;
@@ -398,5 +397,13 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
     }
   }
   if (stats_on) ds_flush_stats(sh_stat, a.stats);
+  // the last CTA out re-arms the ticket counter for the next launch (every CTA has drawn its last ticket by now)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(a.tile_done, 1) == (int)gridDim.x - 1) {
+      *a.tile_counter = 0;
+      *a.tile_done = 0;
+    }
+  }
 }
 

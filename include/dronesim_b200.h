@@ -10,7 +10,9 @@
  *   - plain C, no torch / C++ types; every pointer is either HOST or DEVICE as documented.
  *   - every function returns 0 (DS_OK) or a non-zero ds_status; nothing throws.
  *   - one handle per CUDA device; calls on a handle are stream-ordered, asynchronous, and
- *     not thread-safe.  The handle owns all device state; ds_views() lends pointers that stay
+ *     not thread-safe.  After one warm-up call (lazy allocations) ds_step / ds_physics_step / ds_control_* only enqueue
+ *     kernels, so they can be captured into a CUDA graph and replayed; host-side bookkeeping (step_counter, the
+ *     max_steps predicate, the noise substep index, the trajectory log) advances at capture time only.  The handle owns all device state; ds_views() lends pointers that stay
  *     valid until ds_destroy().
  *   - vehicles are numbered v = env * drones_per_env + slot (env-major).  Quaternions are
  *     xyzw (PyBullet / dronesim/utils/math.py:6,25).  Commands are PWM in [MIN_PWM, MAX_PWM].

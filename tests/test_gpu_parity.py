@@ -964,3 +964,52 @@ def test_hover_settles_and_holds_at_the_reference_control_rate():
     assert err.max() < 1e-3, err.max()
     assert np.abs(st["vel"]).max() < 1e-3 and core.stats()["non_finite"] == 0
     core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA graphs: a captured run of fused steps (an odd number of them, hexa types present -> step + fix-up kernels) can be
+# replayed as is - the tile tickets and the WLS queue re-arm themselves on the device, targets advance through the
+# device-resident waypoint counters.  (Host-side bookkeeping - step_counter, the time-limit predicate, the noise
+# substep index, the Logger - advances at capture time only.)
+# ------------------------------------------------------------------------------------------
+def test_cuda_graph_replay_of_fused_steps():
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.workloads import circle_table
+
+    models = ["hexa_6DOF", "robobee"]
+    E, K = 700, 2  # 1,400 vehicles: a dozen tiles, ragged
+    tab = circle_table(num_wp=240, radius=0.4, z=2.0)
+    rng = np.random.default_rng(91)
+    pos0 = np.zeros((E, 2, 3)) + [[0.0, 0.0, 2.0], [0.0, 0.0, 2.0]] + rng.uniform(-0.05, 0.05, (E, 2, 3))
+    off = np.zeros((E, 2, 3))
+    off[:, 1, 0] = 2.0  # the quad flies the same circle 2 m to the side
+    pos0 += off
+    wp0 = rng.integers(0, 240, (E, 2)).astype(np.int32)
+
+    def fresh():
+        c = SwarmCore(models, E, aggregate_phy_steps=K, ground=True, drag=True)
+        c.reset(pos0, wp0=wp0)
+        return c, c.targets_table(tab, offset=off.reshape(-1, 3))
+
+    eager, tg_e = fresh()
+    eager.step(tg_e, 20)  # 5 warm-up + 3 x 5 replayed
+    graph_core, tg_g = fresh()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        graph_core.step(tg_g, 5)  # warm-up on the capture stream: lazy allocations and attributes happen here
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        graph_core.step(tg_g, 5)
+    # capturing does not execute: the three replays are steps 6-20
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    ve, vg = eager.views(), graph_core.views()
+    for k in ("pos", "quat", "vel", "omega_body", "cmd0123", "cmd45", "wp_counter"):
+        np.testing.assert_array_equal(vg[k].cpu().numpy(), ve[k].cpu().numpy(), err_msg=k)
+    eager.close()
+    graph_core.close()

@@ -100,8 +100,8 @@ SYMBOLS = {
     "ds_log_read": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "ds_step_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_rollout_host": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
-    "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                               C.c_void_p]),
+    "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                               C.c_int32, C.c_void_p]),
     "ds_debug_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "ds_strerror": (C.c_char_p, [C.c_int]),
     "ds_last_cuda_error": (C.c_int, [_H]),

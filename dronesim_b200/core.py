@@ -355,16 +355,17 @@ class SwarmCore:
     def stats_reset(self):
         L.check(L.lib().ds_stats_reset(self._h, self._stream()), self._h)
 
-    def debug_wls(self, type_id: int, v: torch.Tensor, cmd: torch.Tensor, force_slow: bool = False):
-        """Diagnostic: the WLS allocator alone on n problems -> (du [n,6], iterations [n])."""
+    def debug_wls(self, type_id: int, v: torch.Tensor, cmd: torch.Tensor, force_slow: bool = False, working_set: bool = False):
+        """Diagnostic: the WLS allocator alone on n problems -> (du [n,6], iterations [n][, W [n,6]])."""
         v = v.to(self.device, torch.float32).contiguous()
         cmd = cmd.to(self.device, torch.float32).contiguous()
         n = v.shape[0]
         du = torch.empty((n, 6), dtype=torch.float32, device=self.device)
         it = torch.empty((n,), dtype=torch.int32, device=self.device)
-        L.check(L.lib().ds_debug_wls(self._h, int(type_id), self._p(v), self._p(cmd), self._p(du), self._p(it), n,
+        W = torch.zeros((n, 6), dtype=torch.int32, device=self.device)
+        L.check(L.lib().ds_debug_wls(self._h, int(type_id), self._p(v), self._p(cmd), self._p(du), self._p(it), self._p(W), n,
                                      1 if force_slow else 0, self._stream()), self._h)
-        return du, it
+        return (du, it, W) if working_set else (du, it)
 
     # ------------------------------------------------------------------ trajectory capture (Logger layout)
     def log_attach(self, vehicles, capacity: int):

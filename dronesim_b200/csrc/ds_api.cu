@@ -210,15 +210,25 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     const double rc[3] = {h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[0],
                           h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[1],
                           h->cfg.integrator == DS_INTEG_RPY ? 0.0 : p.r_com[2]};
-    for (int i = 0; i < 9; ++i) { d.J[i] = (float)p.J[i]; d.Jinv[i] = (float)Ji[i]; }
+    const double dt = 1.0 / (double)h->cfg.sim_freq;
+    // inertia tensor and J^-1 dt as column pairs + third row (ds_physics.cuh)
+    for (int c = 0; c < 3; ++c) {
+      d.Jc[c] = make_float2((float)p.J[0 * 3 + c], (float)p.J[1 * 3 + c]);
+      d.Jr[c] = (float)p.J[2 * 3 + c];
+      d.Jdc[c] = make_float2((float)(Ji[0 * 3 + c] * dt), (float)(Ji[1 * 3 + c] * dt));
+      d.Jdr[c] = (float)(Ji[2 * 3 + c] * dt);
+    }
     for (int i = 0; i < 3; ++i) d.rc[i] = (float)rc[i];
+    d.nrc_xy = make_float2((float)-rc[0], (float)-rc[1]);
+    d.nrc_z = (float)-rc[2];
     d.has_rc = (rc[0] != 0.0 || rc[1] != 0.0) ? 1 : (rc[2] != 0.0 ? 2 : 0);  // general | along body z only | none
-    d.inv_mass = (float)(1.0 / p.mass);
+    d.dtm = (float)(dt / p.mass);
     d.kf = (float)p.kf;
     d.gnd_k = (float)(p.gnd_eff_coeff * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
     d.gnd_clip = (float)p.gnd_eff_h_clip;
-    for (int i = 0; i < 3; ++i) d.drag_k[i] = (float)(p.drag_coeff[i] * (2.0 * M_PI / 60.0));
-    d.dw_k1 = (float)(p.dw_coeff[0] * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
+    d.ndk_xy = make_float2((float)(-p.drag_coeff[0] * (2.0 * M_PI / 60.0)), (float)(-p.drag_coeff[1] * (2.0 * M_PI / 60.0)));
+    d.ndk_z = (float)(-p.drag_coeff[2] * (2.0 * M_PI / 60.0));
+    d.dw_k1n = (float)(-p.dw_coeff[0] * (p.prop_radius / 4.0) * (p.prop_radius / 4.0));
     // exp(-0.5 (d / beta)^2) = exp2(-(d / beta')^2) with beta' = beta / sqrt(0.5 log2 e)
     const double dw_s = sqrt(0.5 * 1.4426950408889634074);
     d.dw_k2 = (float)(p.dw_coeff[1] / dw_s);
@@ -251,6 +261,12 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
       r.pmin = (float)p.min_pwm[i]; r.pmax = (float)p.max_pwm[i];
       rpm0 += p.pwm2rpm_const[i];
       for (int k = 0; k < 3; ++k) lat[k] += rel[k];
+      // substep-loop copies: rotor heights of rotor pairs, ground-effect wrench pairs
+      float* ghp = reinterpret_cast<float*>(&d.gh[i / 2][0]);
+      for (int k = 0; k < 3; ++k) ghp[2 * k + (i & 1)] = (float)rel[k];
+      d.gw[i][0] = make_float2(r.ax, r.ay);
+      d.gw[i][1] = make_float2(r.az, r.gx);
+      d.gw[i][2] = make_float2(r.gy, r.gz);
       for (int j = 0; j < p.n_v; ++j) d.alloc[i * 6 + j] = (float)p.alloc[i][j];
     }
     d.rpm0_sum = (float)rpm0;
@@ -385,8 +401,14 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.flags = h->cfg.flags & 0xFu;
   a.dt = 1.0f / h->cfg.sim_freq;
   a.gravity = h->cfg.gravity;
+  {
+    const double dt = 1.0 / (double)h->cfg.sim_freq;
+    a.dtg = (float)(dt * (double)h->cfg.gravity);
+    a.qh = (float)(0.25 * dt * dt);
+    a.qk[0] = (float)(0.5 * dt); a.qk[1] = (float)(-dt / 12.0); a.qk[2] = (float)(dt / 240.0); a.qk[3] = (float)(-dt / 10080.0);
+  }
   a.goal_en = h->cfg.done_goal_enable; a.floor_en = h->cfg.done_floor_enable;
-  a.goal_x = h->cfg.goal[0]; a.goal_y = h->cfg.goal[1]; a.goal_z = h->cfg.goal[2]; a.goal_r = h->cfg.goal_radius;
+  a.goal_x = h->cfg.goal[0]; a.goal_y = h->cfg.goal[1]; a.goal_z = h->cfg.goal[2]; a.goal_r2 = h->cfg.goal_radius * h->cfg.goal_radius;
   a.z_min = h->cfg.z_min;
 }
 
@@ -587,7 +609,7 @@ static void obs_args(const ds_handle* h, DsObsArgs& a) {
   a.s_c1 = h->act_valid ? h->s_a1 : h->s_c1;
   a.slot_type = h->d_slot_type; a.types = h->d_types;
   a.n = h->n; a.D = h->cfg.drones_per_env; a.nu6 = h->nu6 ? 1 : 0;
-  a.radius = h->cfg.neighbourhood_radius;
+  a.radius2 = h->cfg.neighbourhood_radius * h->cfg.neighbourhood_radius;
 }
 
 // one Logger sample of the attached vehicles (after a control / physics step); full buffer: samples are dropped
@@ -758,12 +780,12 @@ extern "C" int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t 
 }
 
 extern "C" int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out,
-                            int32_t* iter_out, int32_t n, int32_t force_slow, void* stream) {
+                            int32_t* iter_out, int32_t* w_out, int32_t n, int32_t force_slow, void* stream) {
   if (!h || !v || !cmd || !du_out || !iter_out || n <= 0) return DS_ERR_INVALID;
   if (!h->types_set) return DS_ERR_STATE;
   if (type_id < 0 || type_id >= h->n_types) return DS_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
-  ds_wls_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_types, h->d_wls, type_id, v, cmd, du_out, iter_out, n,
+  ds_wls_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_types, h->d_wls, type_id, v, cmd, du_out, iter_out, w_out, n,
                                                                force_slow);
   h->launches++;
   CK(cudaGetLastError());

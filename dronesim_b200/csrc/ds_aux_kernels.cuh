@@ -85,7 +85,7 @@ struct DsObsArgs {
   float* reward_env;
   int n, D, nu6;
   int reward_mode;  // 0: constant -1 (the reference); 1: -mean |pos_e| of the env
-  float radius;
+  float radius2;  // fl(NEIGHBOURHOOD_RADIUS^2)
 };
 
 // BaseAviary._getDroneStateVector (BaseAviary.py:780-790) of vehicle v, zero padded to 22 floats
@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(256) ds_obs_kernel(const DsObsArgs a) {
       for (int j = 0; j < a.D; ++j) {
         if (j == slot) continue;
         float4 O = a.s_pos[env0 + j];
-        float dx = P.x - O.x, dy = P.y - O.y, dz = P.z - O.z;
-        if (sqrtf(dx * dx + dy * dy + dz * dz) < a.radius) bits |= 1u << j;
+        // |p_i - p_j|^2 < r^2 with every operation correctly rounded in a fixed order (no FMA contraction, no square
+        // root): the bit is a pure function of the FP32 positions, reproduced exactly by the same float32 expression
+        const float dx = P.x - O.x, dy = P.y - O.y, dz = P.z - O.z;
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (d2 < a.radius2) bits |= 1u << j;
       }
       a.neighbors[v] = bits;
     }
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(256) ds_reset_ext_kernel(const DsResetArgs a, 
 // diagnostic: the WLS allocator alone (fast path + FP64 active-set slow path), one problem per thread
 // ---------------------------------------------------------------------------------------------
 __global__ void ds_wls_kernel(const DsTypeDev* types, const DsWlsDev* wls, int type_id, const float* v, const float* cmd,
-                              float* du_out, int* iter_out, int n, int force_slow) {
+                              float* du_out, int* iter_out, int* w_out, int n, int force_slow) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const DsTypeDev& tp = types[type_id];
@@ -291,9 +294,10 @@ __global__ void ds_wls_kernel(const DsTypeDev* types, const DsWlsDev* wls, int t
     const float* a = tp.alloc + k * 6;
     du[k] = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3] + a[4] * nu[4] + a[5] * nu[5];
     float umin = tp.rotor[k].pmin - cmd[6 * i + k], umax = tp.rotor[k].pmax - cmd[6 * i + k];
-    feasible = feasible && !(du[k] >= umax + 1.0f || du[k] <= umin - 1.0f);
+    feasible = feasible && (du[k] < umax + (1.0f - DS_WLS_MARGIN)) && (du[k] > umin - (1.0f - DS_WLS_MARGIN));
   }
   int it = 1;
+  int W[6] = {0, 0, 0, 0, 0, 0};  // a feasible first iterate leaves the working set empty (wls_alloc.py:171)
   if (!feasible || force_slow) {
     double vv[6], umin[6], umax[6], u[6];
     for (int k = 0; k < 6; ++k) {
@@ -302,9 +306,10 @@ __global__ void ds_wls_kernel(const DsTypeDev* types, const DsWlsDev* wls, int t
       umax[k] = P->pmax[k] - (double)cmd[6 * i + k];
       u[k] = 0.0;
     }
-    it = ds_wls_alloc(P, vv, umin, umax, u);
+    it = ds_wls_alloc(P, vv, umin, umax, u, W);
     for (int k = 0; k < 6; ++k) du[k] = (it > 0) ? (float)u[k] : 0.f;
   }
   for (int k = 0; k < 6; ++k) du_out[6 * i + k] = du[k];
   iter_out[i] = it;
+  if (w_out) for (int k = 0; k < 6; ++k) w_out[6 * i + k] = W[k];
 }

@@ -14,6 +14,8 @@
 #include "ds_device.cuh"
 #include "ds_wls.cuh"
 
+#define DS_WLS_MARGIN 1.0e-3f
+
 struct CtrlState {   // kinematic state the controller sees
   float px, py, pz;
   float qx, qy, qz, qw;
@@ -170,7 +172,10 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
         const float* a = tp.alloc + i * 6;
         du[i] = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3] + a[4] * nu[4] + a[5] * nu[5];
         float umin = tp.rotor[i].pmin - m.cmd[i], umax = tp.rotor[i].pmax - m.cmd[i];
-        feasible = feasible && !(du[i] >= umax + 1.0f || du[i] <= umin - 1.0f);  // wls_alloc.py:264
+        // wls_alloc.py:264 decides u_opt >= umax + 1 or u_opt <= umin - 1 in FP64; the FP32 first iterate is trusted only
+        // when it clears the thresholds by DS_WLS_MARGIN (>> its rounding error), anything closer goes to the FP64
+        // active-set routine, whose own first pass repeats the reference's test exactly
+        feasible = feasible && (du[i] < umax + (1.0f - DS_WLS_MARGIN)) && (du[i] > umin - (1.0f - DS_WLS_MARGIN));
       }
       o.wls_iter = 1;
       if (DEFER) {

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ds_lanes.cuh"
+
 // 128 vehicles per tile x 4 resident CTAs per SM (16 warps, 128 registers per thread): with the dynamic tile tickets the
 // smaller tile halves the tail of a launch; measured 1-5 % faster than 256 x 2 on every workload (profiles/r01_notes.md)
 #ifndef DS_TILE
@@ -20,6 +22,7 @@
 #define DS_DW_ROWS (DS_TILE + DS_TILE / 2)       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2
 #define DS_DW_BUF (2 * DS_TILE)                  // rows reserved per snapshot buffer: the symmetric D = 16 variant stores every row twice (DS_TILE / 16 envs x 32 rows)
 
+#define DS_TYPE_PAD 8
 struct __align__(16) DsRotorDev {
   float ax, ay, az, scale;   // thrust axis (body)            | PWM2RPM_SCALE
   float mx, my, mz, cnst;    // torque / unit thrust about CoM = (r - rc) x a + spin (km/kf) t | PWM2RPM_CONST
@@ -28,17 +31,29 @@ struct __align__(16) DsRotorDev {
 };
 
 struct __align__(16) DsTypeDev {
-  DsRotorDev rotor[6];       // 96 floats
-  float J[9];
-  float Jinv[9];
-  float rc[3];
-  float inv_mass;
-  float kf;
-  float gnd_k;               // GND_EFF_COEFF * (PROP_RADIUS/4)^2
+  DsRotorDev rotor[6];       // 96 floats: control-step constants (motor map, clip limits, hoisted rotor wrench)
+  // ---- substep-loop constants, laid out as the register PAIRS the packed FP32 arithmetic (FFMA2) consumes, 16-byte
+  // groups so that one LDS.128 delivers two pairs (ds_physics.cuh)
+  float2 gh[3][3];           // rotor pair p = (2p, 2p+1): (rx, rx'), (ry, ry'), (rz, rz') - two rotor heights per FFMA2
+  float2 gh_pad;
+  float2 gw[6][3];           // rotor i: (ax, ay), (az, gx), (gy, gz) - wrench pairs (Fx,Fy) (Fz,tx) (ty,tz) += g_i * ...
+  float2 Jc[3];              // inertia tensor, column pairs (J00,J10) (J01,J11) (J02,J12)
+  float Jr[3];               // ... and its third row
+  float dtm;                 // TIMESTEP / mass: the velocity update is u += dtm (R F) - TIMESTEP g
+  float2 Jdc[3];             // J^-1 * TIMESTEP in the same layout: the rate update is w += Jd (tau - w x J w)
+  float Jdr[3];
   float gnd_clip;            // GND_EFF_H_CLIP
-  float drag_k[3];           // DRAG_COEFF * 2 pi / 60
-  float dw_k1;               // DW_COEFF_1 * (PROP_RADIUS/4)^2
+  float2 nrc_xy;             // -rc (centre of mass in the base frame): p_base = c - R rc
+  float nrc_z;
+  float dw_k1n;              // -DW_COEFF_1 * (PROP_RADIUS/4)^2
+  float2 ndk_xy;             // -DRAG_COEFF * 2 pi / 60
+  float ndk_z;
+  float kf;
   float dw_k2, dw_k3;        // DW_COEFF_2,3 divided by sqrt(0.5 log2 e): exp(-0.5 (d/beta)^2) = exp2(-(d/beta')^2)
+  float gnd_k;               // GND_EFF_COEFF * (PROP_RADIUS/4)^2
+  float pad0_;
+  // ---- per control step / set-up
+  float rc[3];
   float kp, kd;
   float att[3];
   float rate[3];
@@ -52,7 +67,7 @@ struct __align__(16) DsTypeDev {
   int rotor_model;           // 0 quad (_quad_copter_physics), 1 morphing hexa (_morphing_hexa_physics), 2 quad "advanced" (:1493-1512)
   float kf_over_km;          // turns the stored reaction-torque column (m - g) = spin km/kf t into spin t
   float adv[15];             // rotor_model 2: the 14 oblique-flow coefficients (Data_section5_ObliqueFlow) + propeller radius [m]
-  float pad_[3];        // stride = 200 words = 8 (mod 32): four types sit in disjoint shared-memory banks
+  float pad_[DS_TYPE_PAD];   // stride = 8 (mod 32) words: four types sit in disjoint shared-memory banks
 };
 static_assert(sizeof(DsTypeDev) % 16 == 0, "DsTypeDev must be float4-copyable");
 static_assert((sizeof(DsTypeDev) / 4) % 32 == 8, "DsTypeDev bank stride");
@@ -107,6 +122,9 @@ struct DsArgs {
   int store_act;    // physics stores the clipped action to s_a0/s_a1
   float dt;         // TIMESTEP
   float gravity;
+  float dtg;        // TIMESTEP * gravity
+  float qh;         // 0.25 TIMESTEP^2: (half angle)^2 of a substep = qh |w|^2
+  float qk[4];      // TIMESTEP x Taylor coefficients of 0.5 sin(h)/h in h^2 (ds_quat_step)
   float ctrl_dt, inv_ctrl_dt;
   int ext;          // 1: the EXT kernel variant runs (motor model and / or angular-acceleration filter on)
   float motor_a;    // 1 - exp(-dt / tau_motor); >= 1: static map (BaseAviary.py:1487-1490)
@@ -125,7 +143,7 @@ struct DsArgs {
   const float4* t_off;
   // done predicate
   int goal_en, floor_en, time_hit;
-  float goal_x, goal_y, goal_z, goal_r;
+  float goal_x, goal_y, goal_z, goal_r2;   // goal_r2 = fl(r * r): the predicate compares squared distances
   float z_min;
   // per-env outputs of the fused step (optional, DEVICE): reduced with warp shuffles inside the step kernel when every env
   // sits inside one warp (D | 32); the host falls back to the observation kernel otherwise
@@ -147,10 +165,7 @@ struct DsArgs {
 #define DS_PI_F 3.14159265358979323846f
 #define DS_GIMBAL 0.99999f
 
-// single-instruction MUFU forms (flush-to-zero, ~1 ulp): no denormal pre/post scaling around the SFU op
-__device__ __forceinline__ float ds_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float ds_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float ds_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// single-instruction MUFU forms ds_rcp / ds_ex2 / ds_rsqrt: ds_lanes.cuh
 
 struct Mat3 { float m00, m01, m02, m10, m11, m12, m20, m21, m22; };
 

@@ -170,6 +170,7 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsT
     if (a.t_vel) { float4 q = __ldg(a.t_vel + v); t.vx = q.x; t.vy = q.y; t.vz = q.z; }
     if (a.t_acc) { float4 q = __ldg(a.t_acc + v); t.ax = q.x; t.ay = q.y; t.az = q.z; }
   } else {
+    wp = min(max(wp, 0), a.num_wp - 1);  // a counter left over from a longer table must not read past this one
     const float4* row = a.t_table + 3 * wp;
     float4 p = __ldg(row), q = __ldg(row + 1), r = __ldg(row + 2);
     t.x = p.x; t.y = p.y; t.z = p.z; t.yaw = p.w;
@@ -323,9 +324,12 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
     if (MODE == 1) done_bits = __float_as_uint(sg[SG_LV * T + ld].w);
 
     // ---- done predicate on the fresh state (fly_INDI_TrajectoryTrack.py:249-250)
+    // |pos - goal|^2 < r^2 in a fixed order of correctly rounded operations (no contraction, no square root), so the bit
+    // is a pure function of the FP32 position, reproduced exactly by the same float32 expression
     if (a.goal_en) {
-      float dx = s.px - a.goal_x, dy = s.py - a.goal_y, dz = s.pz - a.goal_z;
-      if (sqrtf(dx * dx + dy * dy + dz * dz) < a.goal_r) done_bits |= 1u;
+      const float dx = s.px - a.goal_x, dy = s.py - a.goal_y, dz = s.pz - a.goal_z;
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d2 < a.goal_r2) done_bits |= 1u;
     }
     if (a.floor_en && s.pz < a.z_min) done_bits |= 2u;
     if (a.time_hit) done_bits |= 4u;

@@ -9,14 +9,24 @@
 // DS_INTEG_QUAT is Newton-Euler about the composite centre of mass with an exponential-map
 // quaternion update (asked by north_star; beyond the reference).
 //
-// The kernel is bound by instruction issue (ncu: issue slots > 80 % busy, DRAM ~ 11 %), so the
-// code below is written to minimise issued instructions per substep:
+// The kernel is bound by instruction issue (ncu: issue slots 81 % busy, FP32 FMA pipe 53 %, DRAM 19 %), and two thirds
+// of its instructions are FP32.  sm_100 has packed FP32 instructions (FFMA2 / FMUL2 / FADD2: two operations per issue
+// slot, same FMA-pipe cycles), so the substep is written on register PAIRS (f2, ds_lanes.cuh) wherever two operations
+// share a shape:
+//  * vectors are (x, y) pairs + a scalar z; the rotation matrix is three column pairs + its third row, so R v is
+//    3 FFMA2 + 3 FFMA instead of 9 FFMA, and the same for J w and J^-1 g (constants stored in that layout);
+//  * the body wrench lives in three pairs (Fx, Fy) (Fz, tx) (ty, tz): every rotor adds its ground-effect force and
+//    torque with 3 FFMA2 (broadcast magnitude) instead of 6 FFMA; the heights of TWO rotors come from 3 FFMA2;
+//  * two downwash partners are evaluated per packed instruction;
+//  * every multiply-add is spelled as ds_fma: the r01 kernel left 34 % FMUL + 18 % FADD unfused.
+// What has no packed form (MUFU, min / max, compares, selects) runs per half on the aliased registers.
+// Unchanged from round 1:
 //  * the command is constant across the K substeps of a control step (BaseAviary.py:507-545), so
 //    the rotor wrench sum_i T_i a_i, sum_i T_i m_i is hoisted out of the substep loop; only the terms
 //    that depend on the moving state (ground effect, drag, downwash, gyroscopic torque) are per substep;
 //  * reciprocal / exp2 / rsqrt are the single-instruction MUFU forms (ds_rcp, ds_ex2, ds_rsqrt);
-//  * the downwash pair term is 19 instructions (see ds_downwash_pair): the Gaussian's 0.5 log2(e) is
-//    folded into the per-type beta coefficients, DW_COEFF_1 is applied once after the neighbour loop;
+//  * the Gaussian's 0.5 log2(e) is folded into the per-type beta coefficients, DW_COEFF_1 is applied once after the
+//    neighbour loop;
 //  * state is integrated in centre-of-mass coordinates; rotor sites are stored relative to the centre
 //    of mass so the ground-effect heights need no base-frame conversion.
 #pragma once
@@ -31,46 +41,76 @@ struct PhysState {
 
 #define DS_DW_PAD 1       // shared-memory position rows are padded to D + 1 float4: envs of a warp hit disjoint banks
 
-__device__ __forceinline__ void ds_quat_step(float& qx, float& qy, float& qz, float& qw, float wx, float wy, float wz,
-                                             float dt) {
-  // q <- normalize(q (x) exp(w dt)); polynomial sin/cos of the half angle (|half| < 0.5), libm beyond
-  float tx = wx * dt, ty = wy * dt, tz = wz * dt;
-  float h2 = 0.25f * (tx * tx + ty * ty + tz * tz);  // (angle/2)^2
-  float k, c;
-  if (h2 < 0.25f) {
-    // Taylor in h2 = (angle/2)^2 < 0.25: the first dropped terms are 5e-9 (sine) and 3e-10 (cosine) relative at h2 = 0.25
-    k = 0.5f + h2 * (-0.5f / 6.0f + h2 * (0.5f / 120.0f + h2 * (-0.5f / 5040.0f)));
-    c = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f))));
-  } else {
-    // |w| dt >= 1 rad per substep (>= 240 rad/s): a blown-up state; MUFU sin / cos keep it finite and this branch free
-    // of libm's argument-reduction slow path (two CALLs inside the substep loop otherwise)
-    float half = sqrtf(h2), s;
-    __sincosf(half, &s, &c);
-    k = 0.5f * s * ds_rcp(half);
-  }
-  float dx = tx * k, dy = ty * k, dz = tz * k, dw = c;
-  float nx = qw * dx + qx * dw + qy * dz - qz * dy;
-  float ny = qw * dy - qx * dz + qy * dw + qz * dx;
-  float nz = qw * dz + qx * dy - qy * dx + qz * dw;
-  float nw = qw * dw - qx * dx - qy * dy - qz * dz;
-  float n = ds_rsqrt(nx * nx + ny * ny + nz * nz + nw * nw);
-  qx = nx * n; qy = ny * n; qz = nz * n; qw = nw * n;
+__device__ __forceinline__ float f2_lo(f2 p) { float a, b; f2_split(p, a, b); return a; }
+__device__ __forceinline__ float f2_hi(f2 p) { float a, b; f2_split(p, a, b); return b; }
+__device__ __forceinline__ f2 ld2(const float2& c) { return f2_make(c.x, c.y); }
+
+// Rotation matrix of a unit quaternion (btMatrix3x3::setRotation, s = 2) as column pairs + third row:
+// c0 = (m00, m10), c1 = (m01, m11), c2 = (m02, m12), r = (m20, m21, m22).  16 FMA-pipe instructions.
+struct RotP { f2 c0, c1, c2; float r0, r1, r2; };
+__device__ __forceinline__ RotP ds_rotp(f2 qxy, f2 qzw) {
+  const float x = f2_lo(qxy), y = f2_hi(qxy), z = f2_lo(qzw), w = f2_hi(qzw);
+  const f2 d2 = qxy + qxy;                   // (2x, 2y)
+  const float x2 = f2_lo(d2), y2 = f2_hi(d2), z2 = z + z;
+  const f2 xz = qxy * z2;                    // (x 2z, y 2z)
+  const f2 sq = qxy * d2;                    // (2xx, 2yy)
+  const float wz2 = w * z2;
+  const float tz = ds_fma(ds_neg(z), z2, 1.0f);
+  RotP R;
+  R.c0 = f2_make(tz - f2_hi(sq), ds_fma(x, y2, wz2));
+  R.c1 = f2_make(ds_fma(x, y2, ds_neg(wz2)), tz - f2_lo(sq));
+  R.c2 = f2_make(ds_fma(w, y2, f2_lo(xz)), ds_fma(ds_neg(w), x2, f2_hi(xz)));
+  R.r0 = ds_fma(ds_neg(w), y2, f2_lo(xz));
+  R.r1 = ds_fma(w, x2, f2_hi(xz));
+  R.r2 = (1.0f - f2_lo(sq)) - f2_hi(sq);
+  return R;
+}
+// acc + R v
+__device__ __forceinline__ void ds_rot_fma(const RotP& R, float vx, float vy, float vz, f2& axy, float& az) {
+  axy = ds_fma(R.c0, vx, ds_fma(R.c1, vy, ds_fma(R.c2, vz, axy)));
+  az = ds_fma(R.r0, vx, ds_fma(R.r1, vy, ds_fma(R.r2, vz, az)));
 }
 
+// q <- normalize(q (x) exp(w dt)).  Taylor polynomials of 0.5 sin(h)/h and cos(h) in h^2 = (half angle)^2 < 0.25 (the
+// first dropped terms are 5e-9 and 3e-10 relative at h^2 = 0.25); a.qk = TIMESTEP x the sine coefficients, a.qh = 0.25 dt^2.
+__device__ __forceinline__ void ds_quat_step(const DsArgs& a, f2& qxy, f2& qzw, f2 wxy, float wz) {
+  const f2 w2 = wxy * wxy;
+  const float h2 = ds_fma(wz, wz, f2_lo(w2) + f2_hi(w2)) * a.qh;
+  float k = ds_fma(h2, ds_fma(h2, ds_fma(h2, a.qk[3], a.qk[2]), a.qk[1]), a.qk[0]);
+  float c = ds_fma(h2, ds_fma(h2, ds_fma(h2, ds_fma(h2, 1.0f / 40320.0f, -1.0f / 720.0f), 1.0f / 24.0f), -0.5f), 1.0f);
+  if (h2 >= 0.25f) {
+    // |w| dt >= 1 rad per substep (>= 240 rad/s): a blown-up state; MUFU sin / cos keep it finite and this branch free
+    // of libm's argument-reduction slow path (two CALLs inside the substep loop otherwise)
+    const float half = sqrtf(h2);
+    float sn;
+    __sincosf(half, &sn, &c);
+    k = 0.5f * a.dt * sn * ds_rcp(half);
+  }
+  const f2 dxy = wxy * k;
+  const float dx = f2_lo(dxy), dy = f2_hi(dxy), dz = wz * k;
+  const float qx = f2_lo(qxy), qy = f2_hi(qxy), qz = f2_lo(qzw), qw = f2_hi(qzw);
+  // (nx, ny) = qw (dx, dy) + c (qx, qy) + (qy dz - qz dy, qz dx - qx dz)
+  f2 nxy = ds_fma(dxy, qw, qxy * c);
+  nxy = f2_make(ds_fma(qy, dz, ds_fma(ds_neg(qz), dy, f2_lo(nxy))), ds_fma(qz, dx, ds_fma(ds_neg(qx), dz, f2_hi(nxy))));
+  // (nz, nw) = c (qz, qw) + (qw dz + qx dy - qy dx, -qz dz - qx dx - qy dy)
+  f2 nzw = qzw * c;
+  nzw = f2_make(ds_fma(qw, dz, ds_fma(qx, dy, ds_fma(ds_neg(qy), dx, f2_lo(nzw)))),
+                ds_fma(ds_neg(qz), dz, ds_fma(ds_neg(qx), dx, ds_fma(ds_neg(qy), dy, f2_hi(nzw)))));
+  const f2 n2 = ds_fma(nzw, nzw, nxy * nxy);
+  const float n = ds_rsqrt(f2_lo(n2) + f2_hi(n2));
+  qxy = nxy * n;
+  qzw = nzw * n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Downwash of every drone of the env on this one (BaseAviary.py:1747-1763), in units of DW_COEFF_1
 // (PROP_RADIUS / 4)^2: sum_j [dz > 0, dxy < 10] exp(-0.5 (dxy / beta)^2) / dz^2, beta = DW2 dz + DW3.
 // row: the env's position snapshot in shared memory; k2, k3 are pre-divided by sqrt(0.5 log2 e).
-// 19 issued instructions per pair: LDS.128, 3 FADD, FMUL+FFMA (dxy^2), FFMA (beta), FMUL+MUFU.RCP (1/dz^2),
-// MUFU.RCP (1/beta), 2 FMUL + MUFU.EX2 (Gaussian), FMUL, 2 FSETP (one predicate), predicated FADD.
 // dz > 0 also drops the drone itself.  beta == 0 (dz = -DW3 / DW2 exactly) gives 1/beta = inf -> exp2(-inf) = 0,
 // the reference's exp(-inf) (BaseAviary.py:1755), with no extra test.
-__device__ __forceinline__ void ds_downwash_pair(float& acc, const float4 o, float px, float py, float pz, float k2,
-                                                 float k3) {
-  const float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
-  const float d2 = fmaf(dy, dy, dx * dx);
-  const float ib = ds_rcp(fmaf(k2, dz, k3));   // 1 / beta'
-  const float idz2 = ds_rcp(dz * dz);          // 1 / dz^2
-  const float w = idz2 * ds_ex2((ib * ib) * -d2);
+// Two partners per evaluation: the six differences are scalar subtractions written into pairs, the rest is packed.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ds_dw_gate(float& acc, float dz, float d2, float w) {
   asm("{\n\t.reg .pred p;\n\t"
       "setp.gt.f32 p, %1, 0f00000000;\n\t"
       "setp.lt.and.f32 p, %2, 0f42C80000, p;\n\t"  // dxy^2 < 100
@@ -78,22 +118,64 @@ __device__ __forceinline__ void ds_downwash_pair(float& acc, const float4 o, flo
       : "+f"(acc)
       : "f"(dz), "f"(d2), "f"(w));
 }
+// symmetric variant: the term goes to whichever vehicle of the pair is the lower one
+__device__ __forceinline__ float ds_dw_gate_sym(float& acc, float dz, float d2, float w) {
+  float theirs;
+  asm("{\n\t.reg .pred p, q;\n\t"
+      "setp.lt.f32 q, %3, 0f42C80000;\n\t"          // dxy^2 < 100
+      "setp.gt.and.f32 p, %2, 0f00000000, q;\n\t"   // partner above me: the term is mine
+      "@p add.f32 %0, %0, %4;\n\t"
+      "setp.lt.and.f32 p, %2, 0f00000000, q;\n\t"   // partner below me: the term is the partner's
+      "selp.f32 %1, %4, 0f00000000, p;\n\t}"
+      : "+f"(acc), "=f"(theirs)
+      : "f"(dz), "f"(d2), "f"(w));
+  return theirs;
+}
+
+// the weights exp2(-(dxy / beta')^2) / dz^2 of two partners oa, ob (before the gates); SYM: beta of the LOWER vehicle
+template <bool SYM>
+__device__ __forceinline__ f2 ds_dw_weight2(const float4 oa, const float4 ob, float px, float py, float pz, float k2, float k3,
+                                            f2& dz, f2& d2) {
+  dz = f2_make(oa.z - pz, ob.z - pz);
+  const f2 dx = f2_make(oa.x - px, ob.x - px), dy = f2_make(oa.y - py, ob.y - py);
+  d2 = ds_fma(dy, dy, dx * dx);
+  const f2 ib = ds_rcp(SYM ? ds_fma(ds_abs(dz), k2, k3) : ds_fma(dz, k2, k3));  // 1 / beta'
+  const f2 idz2 = ds_rcp(dz * dz);                                             // 1 / dz^2
+  return idz2 * ds_ex2(ds_neg((ib * ib) * d2));
+}
+__device__ __forceinline__ float ds_dw_weight1(const float4 o, float px, float py, float pz, float k2, float k3, float& dz,
+                                               float& d2) {
+  dz = o.z - pz;
+  const float dx = o.x - px, dy = o.y - py;
+  d2 = ds_fma(dy, dy, dx * dx);
+  const float ib = ds_rcp(ds_fma(dz, k2, k3));
+  const float idz2 = ds_rcp(dz * dz);
+  return idz2 * ds_ex2(ds_neg((ib * ib) * d2));
+}
 
 __device__ __forceinline__ float ds_downwash_sum(const float4* __restrict__ row, int D, float px, float py, float pz,
                                                  float k2, float k3) {
-  float acc = 0.f;
-#ifndef DS_PAIR_UNROLL
-#define DS_PAIR_UNROLL 16
-#endif
-  constexpr int kUnroll = DS_PAIR_UNROLL;
+  float acc0 = 0.f, acc1 = 0.f;
+  auto two = [&](int j) {
+    f2 dz, d2;
+    const f2 w = ds_dw_weight2<false>(row[j], row[j + 1], px, py, pz, k2, k3, dz, d2);
+    ds_dw_gate(acc0, f2_lo(dz), f2_lo(d2), f2_lo(w));
+    ds_dw_gate(acc1, f2_hi(dz), f2_hi(d2), f2_hi(w));
+  };
   if (D == 16) {  // BASELINE configs[3]/[4]
-#pragma unroll kUnroll
-    for (int j = 0; j < 16; ++j) ds_downwash_pair(acc, row[j], px, py, pz, k2, k3);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) two(j);
   } else {
-#pragma unroll 4
-    for (int j = 0; j < D; ++j) ds_downwash_pair(acc, row[j], px, py, pz, k2, k3);
+    int j = 0;
+#pragma unroll 2
+    for (; j + 1 < D; j += 2) two(j);
+    if (j < D) {
+      float dz, d2;
+      const float w = ds_dw_weight1(row[j], px, py, pz, k2, k3, dz, d2);
+      ds_dw_gate(acc0, dz, d2, w);
+    }
   }
-  return acc;
+  return acc0 + acc1;
 }
 
 // ---- symmetric variant (D == 16, every type shares DW_COEFF_2 / DW_COEFF_3 - true of all shipped URDFs) ----------
@@ -101,49 +183,27 @@ __device__ __forceinline__ float ds_downwash_sum(const float4* __restrict__ row,
 // positions and (k2, k3) alone, so each of the 120 unordered pairs of an env is evaluated ONCE: in round r = 1..7
 // slot s evaluates the pair (s, s + r mod 16), keeps the term if it is the lower one, otherwise hands it to the
 // partner by a 16-lane-wide SHFL.IDX; round 8 pairs (s, s + 8) are evaluated from both sides and kept locally.
-// 7 x 22 + 17 issued instructions and 24 MUFU per substep instead of 16 x 19 and 48.  The env's snapshot rows are
-// stored twice (rows s and s + 16 of a 32-row block) so the partner row s + r needs no wrap-around arithmetic.
+// Rounds (1,2) (3,4) (5,6) (7,8) share their packed arithmetic.  The env's snapshot rows are stored twice (rows s and
+// s + 16 of a 32-row block) so the partner row s + r needs no wrap-around arithmetic.
 #define DS_DW_SYM_ROWS 32
-template <bool SEND>
-__device__ __forceinline__ float ds_downwash_pair_sym(float& acc, const float4 o, float px, float py, float pz, float k2,
-                                                      float k3) {
-  const float dz = o.z - pz, dx = o.x - px, dy = o.y - py;
-  const float d2 = fmaf(dy, dy, dx * dx);
-  const float ib = ds_rcp(fmaf(k2, fabsf(dz), k3));  // 1 / beta' of the lower vehicle (its dz is |dz|)
-  const float idz2 = ds_rcp(dz * dz);
-  const float w = idz2 * ds_ex2((ib * ib) * -d2);
-  float theirs = 0.f;
-  if (SEND) {
-    asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.lt.f32 q, %3, 0f42C80000;\n\t"          // dxy^2 < 100
-        "setp.gt.and.f32 p, %2, 0f00000000, q;\n\t"   // partner above me: the term is mine
-        "@p add.f32 %0, %0, %4;\n\t"
-        "setp.lt.and.f32 p, %2, 0f00000000, q;\n\t"   // partner below me: the term is the partner's
-        "selp.f32 %1, %4, 0f00000000, p;\n\t}"
-        : "+f"(acc), "=f"(theirs)
-        : "f"(dz), "f"(d2), "f"(w));
-  } else {
-    asm("{\n\t.reg .pred p;\n\t"
-        "setp.gt.f32 p, %1, 0f00000000;\n\t"
-        "setp.lt.and.f32 p, %2, 0f42C80000, p;\n\t"
-        "@p add.f32 %0, %0, %3;\n\t}"
-        : "+f"(acc)
-        : "f"(dz), "f"(d2), "f"(w));
-  }
-  return theirs;
-}
-
 // row: this thread's own row (slot) in the env's 32-row block; slot16 = slot + 16
 __device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict__ row, int slot16, float px, float py,
                                                        float pz, float k2, float k3) {
-  float acc = 0.f, recv = 0.f;
+  float acc0 = 0.f, acc1 = 0.f, recv0 = 0.f, recv1 = 0.f;
 #pragma unroll
-  for (int r = 1; r <= 7; ++r) {
-    const float theirs = ds_downwash_pair_sym<true>(acc, row[r], px, py, pz, k2, k3);
-    recv += __shfl_sync(0xffffffffu, theirs, slot16 - r, 16);  // from slot - r (mod 16) of my env
+  for (int r = 1; r <= 7; r += 2) {
+    f2 dz, d2;
+    const f2 w = ds_dw_weight2<true>(row[r], row[r + 1], px, py, pz, k2, k3, dz, d2);
+    const float t0 = ds_dw_gate_sym(acc0, f2_lo(dz), f2_lo(d2), f2_lo(w));
+    recv0 += __shfl_sync(0xffffffffu, t0, slot16 - r, 16);  // from slot - r (mod 16) of my env
+    if (r < 7) {
+      const float t1 = ds_dw_gate_sym(acc1, f2_hi(dz), f2_hi(d2), f2_hi(w));
+      recv1 += __shfl_sync(0xffffffffu, t1, slot16 - r - 1, 16);
+    } else {
+      ds_dw_gate(acc1, f2_hi(dz), f2_hi(d2), f2_hi(w));  // round 8: evaluated from both sides, kept locally
+    }
   }
-  ds_downwash_pair_sym<false>(acc, row[8], px, py, pz, k2, k3);
-  return acc + recv;
+  return (acc0 + acc1) + (recv0 + recv1);
 }
 
 // act[] must already be clipped.  prev_rpm_sum: in = sum of rpm of the previously applied action
@@ -171,46 +231,52 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   const bool rc_gen = rc_kind == 1;
 
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
-  const float rc2x = 2.0f * rcx, rc2y = 2.0f * rcy, rc2z = 2.0f * rcz;
 
   float roll = 0.f, pitch = 0.f, yaw = 0.f;
   if (INTEG == 1) ds_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);  // state cache rpy (BaseAviary.py:729)
 
-  // R rc and R (w x rc) for the current attitude / rates
-  auto rot_rc = [&](const Mat3& R, float& ox, float& oy, float& oz) {
-    ox = R.m02 * rcz; oy = R.m12 * rcz; oz = R.m22 * rcz;
+  // state as pairs: centre-of-mass position c, velocity u (QUAT: of the centre of mass), body rates w, quaternion
+  f2 cxy = f2_make(s.px, s.py), uxy = f2_make(s.vx, s.vy), wxy = f2_make(s.wx, s.wy);
+  f2 qxy = f2_make(s.qx, s.qy), qzw = f2_make(s.qz, s.qw);
+  float cz = s.pz, uz = s.vz, wz = s.wz;
+
+  // acc + sign R (w x rc): sign = -1 gives the velocity of the base origin from the centre-of-mass velocity
+  auto add_rot_wxrc = [&](const RotP& R, float sign, f2& vxy, float& vz) {
+    const float zc = sign * rcz;
+    float kx = f2_hi(wxy) * zc, ky = f2_lo(wxy) * ds_neg(zc);  // sign (w x rc), rc along z
     if (rc_gen) {
-      ox += R.m00 * rcx + R.m01 * rcy; oy += R.m10 * rcx + R.m11 * rcy; oz += R.m20 * rcx + R.m21 * rcy;
+      const float xc = sign * rcx, yc = sign * rcy;
+      kx = ds_fma(wz, ds_neg(yc), kx); ky = ds_fma(wz, xc, ky);
+      const float kz = ds_fma(f2_lo(wxy), yc, ds_neg(f2_hi(wxy) * xc));
+      ds_rot_fma(R, kx, ky, kz, vxy, vz);
+    } else {
+      vxy = ds_fma(R.c0, kx, ds_fma(R.c1, ky, vxy));
+      vz = ds_fma(R.r0, kx, ds_fma(R.r1, ky, vz));
     }
   };
-  auto rot_wxrc = [&](const Mat3& R, float& ox, float& oy, float& oz) {
-    float kx = s.wy * rcz, ky = -s.wx * rcz;  // w x rc, rc along z
+  // acc + sign R rc
+  auto add_rot_rc = [&](const RotP& R, float sign, f2& pxy, float& pz) {
+    pxy = ds_fma(R.c2, sign * rcz, pxy); pz = ds_fma(R.r2, sign * rcz, pz);
     if (rc_gen) {
-      kx -= s.wz * rcy; ky += s.wz * rcx;
-      const float kz = s.wx * rcy - s.wy * rcx;
-      ox = R.m00 * kx + R.m01 * ky + R.m02 * kz; oy = R.m10 * kx + R.m11 * ky + R.m12 * kz;
-      oz = R.m20 * kx + R.m21 * ky + R.m22 * kz;
-    } else {
-      ox = R.m00 * kx + R.m01 * ky; oy = R.m10 * kx + R.m11 * ky; oz = R.m20 * kx + R.m21 * ky;
+      pxy = ds_fma(R.c0, sign * rcx, ds_fma(R.c1, sign * rcy, pxy));
+      pz = ds_fma(R.r0, sign * rcx, ds_fma(R.r1, sign * rcy, pz));
     }
   };
 
-  // QUAT: integrate centre-of-mass position / velocity
-  float cx = s.px, cy = s.py, cz = s.pz, ux = s.vx, uy = s.vy, uz = s.vz;
   if (has_rc) {
-    const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    float ox, oy, oz;
-    rot_rc(R, ox, oy, oz);
-    cx += ox; cy += oy; cz += oz;
-    rot_wxrc(R, ox, oy, oz);
-    ux += ox; uy += oy; uz += oz;
+    const RotP R = ds_rotp(qxy, qzw);
+    add_rot_rc(R, 1.0f, cxy, cz);
+    add_rot_wxrc(R, 1.0f, uxy, uz);
   }
   // ---- rotor thrusts and the rotor part of the body wrench: once per control step (the command is constant across
-  // the substeps), or once per substep when the motor model moves the rotor speeds
-  float Tg[NU];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2: the only per-rotor value the substeps need
-  float rpm_sum = 0.f, F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f;
+  // the substeps), or once per substep when the motor model moves the rotor speeds.  The wrench is kept as the three
+  // pairs (Fx, Fy) (Fz, tx) (ty, tz).
+  f2 Tg[NU / 2];  // T_i * GND_EFF_COEFF (PROP_RADIUS/4)^2 of two rotors: the only per-rotor value the substeps need
+  float rpm_sum = 0.f;
+  f2 W0_0, W1_0, W2_0;
   auto rotor_wrench = [&](int k) {
-    rpm_sum = 0.f; F0x = 0.f; F0y = 0.f; F0z = 0.f; t0x = 0.f; t0y = 0.f; t0z = 0.f;
+    float F0x = 0.f, F0y = 0.f, F0z = 0.f, t0x = 0.f, t0y = 0.f, t0z = 0.f, tg[NU];
+    rpm_sum = 0.f;
     // rotor noise (EXT; BaseAviary.py:1429-1432, 1518-1525): per substep N(0, sigma_f) on every thrust, N(0, sigma_m) on
     // every reaction torque; the quad model also puts (f_noise[0], f_noise[1]) on every rotor link laterally and
     // (m_noise[0], m_noise[1]) on the base (:1528-1543).  Ground effect keeps the noise-free thrust (:1680-1685).
@@ -230,13 +296,17 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
     const bool adv = EXT && tp.rotor_model == 2;
     float adv_vs = 0.f, adv_vc = 0.f, adv_cp = 1.f, adv_sp = 0.f;  // V sin(beta), V cos(beta), cos(psi), sin(psi)
     if (adv) {
-      const Mat3 Ra = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-      float vx = ux, vy = uy, vz = uz;
-      if (has_rc) { float ox, oy, oz; rot_wxrc(Ra, ox, oy, oz); vx -= ox; vy -= oy; vz -= oz; }
+      const RotP Ra = ds_rotp(qxy, qzw);
+      f2 vxy = uxy;
+      float vz = uz;
+      if (has_rc) add_rot_wxrc(Ra, -1.0f, vxy, vz);
+      float vx = f2_lo(vxy), vy = f2_hi(vxy);
       const float V = sqrtf(vx * vx + vy * vy + vz * vz);
       if (!(V > 0.1f)) { vx = 0.1f; vy = 0.f; vz = 0.f; }  // :1585-1589
-      const float bx = Ra.m00 * vx + Ra.m01 * vy + Ra.m02 * vz, by = Ra.m10 * vx + Ra.m11 * vy + Ra.m12 * vz;
-      const float bz = Ra.m20 * vx + Ra.m21 * vy + Ra.m22 * vz;
+      f2 bxy = f2_make(0.f, 0.f);
+      float bz = 0.f;
+      ds_rot_fma(Ra, vx, vy, vz, bxy, bz);
+      const float bx = f2_lo(bxy), by = f2_hi(bxy);
       const float cb = ds_clampf(bz * rsqrtf(bx * bx + by * by + bz * bz), -1.f, 1.f);  // cos(beta), beta = arccos (:1600)
       adv_vc = V * cb; adv_vs = V * sqrtf(fmaxf(1.f - cb * cb, 0.f));
       if (bx > 0.1f) {  // psi = arctan(by / bx) (:1603-1605): cos > 0
@@ -254,7 +324,7 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
       }
       rpm_sum += rpm;
       float T = tp.kf * rpm * rpm;                // :1515
-      Tg[i] = T * tp.gnd_k;
+      tg[i] = T * tp.gnd_k;
       if (adv) {
         if (i < tp.n_u) {
           const float* c = tp.adv;  // CstaticFT k1 k2 k3 k4 k5 CstaticMQ k6 k7 k8 k9 k10 k11 k12 | radius
@@ -281,118 +351,131 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
         t0x += nf * r.gx + nm * (r.mx - r.gx); t0y += nf * r.gy + nm * (r.my - r.gy); t0z += nf * r.gz + nm * (r.mz - r.gz);
       }
     }
+#pragma unroll
+    for (int p = 0; p < NU / 2; ++p) Tg[p] = f2_make(tg[2 * p], tg[2 * p + 1]);
+    W0_0 = f2_make(F0x, F0y); W1_0 = f2_make(F0z, t0x); W2_0 = f2_make(t0y, t0z);
   };
   if (!EXT) rotor_wrench(0);
   // drag coefficient x rotor speed sum: the first substep still sees the previously applied action (:532,:545)
-  const float dk0 = -tp.drag_k[0], dk1 = -tp.drag_k[1], dk2 = -tp.drag_k[2];
+  const f2 ndk_xy = ld2(tp.ndk_xy);
+  const float ndk_z = tp.ndk_z;
 
   for (int k = 0; k < a.K; ++k) {
     if (EXT) {  // drag sees the rotor speeds before this substep's motor update
       if (k > 0) prev_rpm_sum = rpm_sum;
       rotor_wrench(k);
     }
-    // ---- downwash first (BaseAviary.py:1747-1763): it needs the base-frame origin only, so the rotation matrix
-    // does not have to stay live (or be rematerialised) across the unrolled pair loop
+    const RotP R = ds_rotp(qxy, qzw);
+    // ---- downwash (BaseAviary.py:1747-1763): every drone of the env reads the same position snapshot
     float dw_fz = 0.f;
-    if (DW) {  // every drone of the env reads the same position snapshot
-      float px = cx, py = cy, pz = cz;  // base-frame origin
-      if (has_rc) {  // R rc by the quaternion sandwich rc + w t + qv x t, t = 2 qv x rc: 15 operations, no matrix
-        const float t0 = s.qy * rc2z - s.qz * rc2y, t1 = s.qz * rc2x - s.qx * rc2z, t2 = s.qx * rc2y - s.qy * rc2x;
-        px -= fmaf(s.qw, t0, rcx) + (s.qy * t2 - s.qz * t1);
-        py -= fmaf(s.qw, t1, rcy) + (s.qz * t0 - s.qx * t2);
-        pz -= fmaf(s.qw, t2, rcz) + (s.qx * t1 - s.qy * t0);
-      }
+    if (DW) {
+      f2 pxy = cxy;  // base-frame origin p = c - R rc
+      float pz = cz;
+      if (has_rc) add_rot_rc(R, -1.0f, pxy, pz);
+      const float px = f2_lo(pxy), py = f2_hi(pxy);
       float dsum;
       float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
+      const float4 me = make_float4(px, py, pz, 0.f);
       if (DW == 2) {  // symmetric pairs: env_row0 / my_row index 32-row blocks, slot = my_row - env_row0
-        const float4 me = make_float4(px, py, pz, 0.f);
         buf[my_row] = me;
         if (my_row - env_row0 < 8) buf[my_row + 16] = me;
         __syncwarp();
         dsum = ds_downwash_sum_sym16(buf + my_row, my_row - env_row0 + 16, px, py, pz, tp.dw_k2, tp.dw_k3);
       } else {
-        buf[my_row] = make_float4(px, py, pz, 0.f);
+        buf[my_row] = me;
         if (WARPSYNC) __syncwarp(); else __syncthreads();
         dsum = ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
       }
-      dw_fz = -tp.dw_k1 * dsum;
+      dw_fz = dsum * tp.dw_k1n;
     }
 
-    const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    float Fx = F0x, Fy = F0y, Fz = F0z + dw_fz, tx = t0x, ty = t0y, tz = t0z;
-    if (DW && rc_gen) { tx += -rcy * dw_fz; ty += rcx * dw_fz; }  // (-rc) x (0, 0, f)
+    // body wrench (Fx, Fy) (Fz, tx) (ty, tz): rotors + downwash force at the base origin, torque (-rc) x (0, 0, f)
+    f2 W0 = W0_0, W1 = W1_0, W2 = W2_0;
+    if (DW) {
+      if (rc_gen) { W1 = ds_fma(f2_make(1.0f, ds_neg(rcy)), dw_fz, W1); W2 = f2_make(ds_fma(dw_fz, rcx, f2_lo(W2)), f2_hi(W2)); }
+      else W1 = f2_make(f2_lo(W1) + dw_fz, f2_hi(W1));
+    }
 
     if (gnd) {  // BaseAviary.py:1672-1699; rotor sites are stored relative to the centre of mass
-      bool gate;
-      if (INTEG == 1) gate = (fabsf(roll) < 0.5f * DS_PI_F) && (fabsf(pitch) < 0.5f * DS_PI_F);
-      else gate = (R.m22 > 0.f) && (fabsf(R.m20) < DS_GIMBAL);  // |roll| < pi/2 <=> cos(roll)cos(pitch) > 0
-      const float gsel = gate ? 1.f : 0.f;  // branch-free: the gate is false only for an inverted vehicle
+      // gate (|roll|, |pitch| < pi/2): a vehicle outside it gets "infinite" rotor heights -> 1/h = 0 (flushed), g = 0
+      float czg;
+      if (INTEG == 1) czg = ((fabsf(roll) < 0.5f * DS_PI_F) && (fabsf(pitch) < 0.5f * DS_PI_F)) ? cz : 3.0e38f;
+      else czg = ((R.r2 > 0.f) && (ds_abs(R.r0) < DS_GIMBAL)) ? cz : 3.0e38f;  // |roll| < pi/2 <=> cos(roll)cos(pitch) > 0
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        const DsRotorDev& r = tp.rotor[i];
-        float h = fmaf(R.m20, r.rx, fmaf(R.m21, r.ry, fmaf(R.m22, r.rz, cz)));
-        float ih = ds_rcp(fmaxf(h, tp.gnd_clip));
-        float g = (Tg[i] * ih) * (ih * gsel);
-        Fx = fmaf(g, r.ax, Fx); Fy = fmaf(g, r.ay, Fy); Fz = fmaf(g, r.az, Fz);
-        tx = fmaf(g, r.gx, tx); ty = fmaf(g, r.gy, ty); tz = fmaf(g, r.gz, tz);
+      for (int p = 0; p < NU / 2; ++p) {
+        const f2 h = ds_fma(ld2(tp.gh[p][0]), R.r0, ds_fma(ld2(tp.gh[p][1]), R.r1, ds_fma(ld2(tp.gh[p][2]), R.r2, czg)));
+        const f2 ih = ds_rcp(ds_max(h, tp.gnd_clip));
+        const f2 g = Tg[p] * (ih * ih);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float gi = j ? f2_hi(g) : f2_lo(g);
+          const float2* c = tp.gw[2 * p + j];
+          W0 = ds_fma(ld2(c[0]), gi, W0); W1 = ds_fma(ld2(c[1]), gi, W1); W2 = ds_fma(ld2(c[2]), gi, W2);
+        }
       }
     }
     if (drag) {  // BaseAviary.py:1719-1732
-      float vx = ux, vy = uy, vz = uz;
-      if (has_rc) {  // velocity of the base origin
-        float ox, oy, oz;
-        rot_wxrc(R, ox, oy, oz);
-        vx -= ox; vy -= oy; vz -= oz;
-      }
+      f2 vxy = uxy;
+      float vz = uz;
+      if (has_rc) add_rot_wxrc(R, -1.0f, vxy, vz);  // velocity of the base origin
       const float sum = (EXT || k == 0) ? prev_rpm_sum : rpm_sum;
-      float d0 = (dk0 * sum) * vx, d1 = (dk1 * sum) * vy, d2 = (dk2 * sum) * vz;
-      float fx = R.m00 * d0 + R.m01 * d1 + R.m02 * d2;
-      float fy = R.m10 * d0 + R.m11 * d1 + R.m12 * d2;
-      float fz = R.m20 * d0 + R.m21 * d1 + R.m22 * d2;
-      Fx += fx; Fy += fy; Fz += fz;
+      const f2 dxy = (ndk_xy * sum) * vxy;
+      const float d2 = (ndk_z * sum) * vz;
+      f2 fxy = R.c2 * d2;
+      float fz = R.r2 * d2;
+      fxy = ds_fma(R.c0, f2_lo(dxy), ds_fma(R.c1, f2_hi(dxy), fxy));
+      fz = ds_fma(R.r0, f2_lo(dxy), ds_fma(R.r1, f2_hi(dxy), fz));
+      W0 += fxy;
+      float Fz = f2_lo(W1) + fz, tx = f2_hi(W1), ty = f2_lo(W2), tz = f2_hi(W2);
       if (has_rc) {  // (-rc) x f
-        tx = fmaf(rcz, fy, tx); ty = fmaf(-rcz, fx, ty);
-        if (rc_gen) { tx += -rcy * fz; ty += rcx * fz; tz += -rcx * fy + rcy * fx; }
+        const float fx = f2_lo(fxy), fy = f2_hi(fxy);
+        tx = ds_fma(fy, rcz, tx); ty = ds_fma(fx, ds_neg(rcz), ty);
+        if (rc_gen) { tx = ds_fma(fz, ds_neg(rcy), tx); ty = ds_fma(fz, rcx, ty); tz = ds_fma(fx, rcy, ds_fma(fy, ds_neg(rcx), tz)); }
       }
+      W1 = f2_make(Fz, tx); W2 = f2_make(ty, tz);
     }
 
-    // ---- Newton-Euler (BaseAviary.py:1790-1807)
-    float awx = (R.m00 * Fx + R.m01 * Fy + R.m02 * Fz) * tp.inv_mass;
-    float awy = (R.m10 * Fx + R.m11 * Fy + R.m12 * Fz) * tp.inv_mass;
-    float awz = (R.m20 * Fx + R.m21 * Fy + R.m22 * Fz) * tp.inv_mass - a.gravity;
-    const float* J = tp.J;
-    const float* Ji = tp.Jinv;
-    float jx = J[0] * s.wx + J[1] * s.wy + J[2] * s.wz;
-    float jy = J[3] * s.wx + J[4] * s.wy + J[5] * s.wz;
-    float jz = J[6] * s.wx + J[7] * s.wy + J[8] * s.wz;
-    float gx = tx - (s.wy * jz - s.wz * jy);
-    float gy = ty - (s.wz * jx - s.wx * jz);
-    float gz = tz - (s.wx * jy - s.wy * jx);
-    float wdx = Ji[0] * gx + Ji[1] * gy + Ji[2] * gz;
-    float wdy = Ji[3] * gx + Ji[4] * gy + Ji[5] * gz;
-    float wdz = Ji[6] * gx + Ji[7] * gy + Ji[8] * gz;
-    // ---- semi-implicit Euler (:1809-1812)
-    ux = fmaf(dt, awx, ux); uy = fmaf(dt, awy, uy); uz = fmaf(dt, awz, uz);
-    s.wx = fmaf(dt, wdx, s.wx); s.wy = fmaf(dt, wdy, s.wy); s.wz = fmaf(dt, wdz, s.wz);
-    cx = fmaf(dt, ux, cx); cy = fmaf(dt, uy, cy); cz = fmaf(dt, uz, cz);
+    // ---- Newton-Euler + semi-implicit Euler (BaseAviary.py:1790-1812): u += (dt / m) R F - dt g, w += dt J^-1 (tau - w x J w)
+    {
+      f2 axy = f2_make(0.f, 0.f);
+      float az = 0.f;
+      const float Fx = f2_lo(W0), Fy = f2_hi(W0), Fz = f2_lo(W1);
+      axy = ds_fma(R.c0, Fx, ds_fma(R.c1, Fy, R.c2 * Fz));
+      az = ds_fma(R.r0, Fx, ds_fma(R.r1, Fy, R.r2 * Fz));
+      uxy = ds_fma(axy, tp.dtm, uxy);
+      uz = ds_fma(az, tp.dtm, uz) - a.dtg;
+    }
+    {
+      const float wx = f2_lo(wxy), wy = f2_hi(wxy);
+      const f2 jxy = ds_fma(ld2(tp.Jc[0]), wx, ds_fma(ld2(tp.Jc[1]), wy, ld2(tp.Jc[2]) * wz));
+      const float jz = ds_fma(tp.Jr[0], wx, ds_fma(tp.Jr[1], wy, tp.Jr[2] * wz));
+      const float jx = f2_lo(jxy), jy = f2_hi(jxy);
+      const float gx = ds_fma(wz, jy, ds_fma(ds_neg(wy), jz, f2_hi(W1)));
+      const float gy = ds_fma(wx, jz, ds_fma(ds_neg(wz), jx, f2_lo(W2)));
+      const float gz = ds_fma(wy, jx, ds_fma(ds_neg(wx), jy, f2_hi(W2)));
+      wxy = ds_fma(ld2(tp.Jdc[0]), gx, ds_fma(ld2(tp.Jdc[1]), gy, ds_fma(ld2(tp.Jdc[2]), gz, wxy)));
+      wz = ds_fma(tp.Jdr[0], gx, ds_fma(tp.Jdr[1], gy, ds_fma(tp.Jdr[2], gz, wz)));
+    }
+    cxy = ds_fma(uxy, dt, cxy);
+    cz = ds_fma(uz, dt, cz);
     if (INTEG == 1) {
-      roll = fmaf(dt, s.wx, roll); pitch = fmaf(dt, s.wy, pitch); yaw = fmaf(dt, s.wz, yaw);
+      roll = fmaf(dt, f2_lo(wxy), roll); pitch = fmaf(dt, f2_hi(wxy), pitch); yaw = fmaf(dt, wz, yaw);
       float4 q = ds_quat_from_euler(roll, pitch, yaw);  // :1817
-      s.qx = q.x; s.qy = q.y; s.qz = q.z; s.qw = q.w;
-      ds_euler(s.qx, s.qy, s.qz, s.qw, roll, pitch, yaw);  // state refresh (:729)
+      qxy = f2_make(q.x, q.y); qzw = f2_make(q.z, q.w);
+      ds_euler(q.x, q.y, q.z, q.w, roll, pitch, yaw);  // state refresh (:729)
     } else {
-      ds_quat_step(s.qx, s.qy, s.qz, s.qw, s.wx, s.wy, s.wz, dt);
+      ds_quat_step(a, qxy, qzw, wxy, wz);
     }
   }
   // back to base-frame origin
-  s.px = cx; s.py = cy; s.pz = cz; s.vx = ux; s.vy = uy; s.vz = uz;
   if (has_rc) {
-    const Mat3 R = ds_rot(s.qx, s.qy, s.qz, s.qw, 2.0f);
-    float ox, oy, oz;
-    rot_rc(R, ox, oy, oz);
-    s.px -= ox; s.py -= oy; s.pz -= oz;
-    rot_wxrc(R, ox, oy, oz);
-    s.vx -= ox; s.vy -= oy; s.vz -= oz;
+    const RotP R = ds_rotp(qxy, qzw);
+    add_rot_rc(R, -1.0f, cxy, cz);
+    add_rot_wxrc(R, -1.0f, uxy, uz);
   }
+  s.px = f2_lo(cxy); s.py = f2_hi(cxy); s.pz = cz;
+  s.vx = f2_lo(uxy); s.vy = f2_hi(uxy); s.vz = uz;
+  s.wx = f2_lo(wxy); s.wy = f2_hi(wxy); s.wz = wz;
+  s.qx = f2_lo(qxy); s.qy = f2_hi(qxy); s.qz = f2_lo(qzw); s.qw = f2_hi(qzw);
   prev_rpm_sum = rpm_sum;
 }

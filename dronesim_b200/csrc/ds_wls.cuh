@@ -57,8 +57,9 @@ static __device__ __noinline__ void ds_lstsq_qr(double* A, double* b, int n_c, i
 }
 
 // returns the iteration count, or -iterations on non-convergence (reference returns None, :350)
+// W_out (nullable): the final working set W in {-1, 0, +1} per actuator (wls_alloc.py:171, 284, 335-338)
 static __device__ __noinline__ int ds_wls_alloc(const DsWlsDev* __restrict__ P, const double* v, const double* umin,
-                                         const double* umax, double* u_out) {
+                                         const double* umax, double* u_out, int* W_out = nullptr) {
   const int n_u = P->n_u, n_v = P->n_v, n_c = n_u + n_v;
   double A[WLS_NC * WLS_NU];       // row-major [n_c][6]
   double A_free[WLS_NC * WLS_NU];  // row-major [n_c][6]
@@ -135,6 +136,7 @@ static __device__ __noinline__ int ds_wls_alloc(const DsWlsDev* __restrict__ P, 
       }
       if (break_flag) {
         for (int i = 0; i < n_u; ++i) u_out[i] = u[i];
+        if (W_out) for (int i = 0; i < n_u; ++i) W_out[i] = (int)W[i];
         return iter;
       }
       // falls through with the previous alpha / id_alpha, as the reference does
@@ -160,12 +162,16 @@ static __device__ __noinline__ int ds_wls_alloc(const DsWlsDev* __restrict__ P, 
     {
       int lk = free_index_lookup[id_alpha];
       if (lk < 0) lk += n_u;  // numpy negative index wraps (only reachable on the stale-alpha path)
-      if (n_free < 0) { return -iter; }
+      if (n_free < 0) {
+        if (W_out) for (int i = 0; i < n_u; ++i) W_out[i] = (int)W[i];
+        return -iter;
+      }
       free_index[lk] = free_index[n_free];
       int moved = free_index[lk];
       free_index_lookup[moved] = free_index_lookup[id_alpha];
       free_index_lookup[id_alpha] = -1;
     }
   }
+  if (W_out) for (int i = 0; i < n_u; ++i) W_out[i] = (int)W[i];
   return -iter;
 }

@@ -263,10 +263,11 @@ int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t n_steps, ui
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* The 6-DOF allocation alone: wls_alloc(v, MIN-cmd, MAX-cmd, G1/0.05, None, None, Wv, 1, None)
  * (INDIControl_6DOF.py:607-628 -> wls_alloc.py:125-350) for n independent problems of type type_id.
- * DEVICE v [n][6], cmd [n][6] -> du_out [n][6], iter_out [n] (iterations; negative = non-convergence).
+ * DEVICE v [n][6], cmd [n][6] -> du_out [n][6], iter_out [n] (iterations; negative = non-convergence),
+ * w_out [n][6] or NULL (the final working set W in {-1, 0, +1}, wls_alloc.py:171, 284, 335-338).
  * force_slow != 0 skips the closed-form first iteration and always runs the FP64 active-set loop. */
 int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out, int32_t* iter_out,
-                 int32_t n, int32_t force_slow, void* stream);
+                 int32_t* w_out, int32_t n, int32_t force_slow, void* stream);
 
 /* FP32 issue-rate micro-benchmark (bench bookkeeping: the FP32 roofline denominator, which
  * MEASURED_PEAKS.json does not carry).  Runs 8 independent FFMA chains per thread on every SM of

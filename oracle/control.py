@@ -56,10 +56,11 @@ def norm_ang(x):
 
 
 # ---------------------------------------------------------------- wls_alloc.py
-def wls_alloc(v, umin, umax, B, u_guess, W_init, Wv, Wu, up, gamma_sq=100000, imax=100):
+def wls_alloc(v, umin, umax, B, u_guess, W_init, Wv, Wu, up, gamma_sq=100000, imax=100, return_W=False):
     """wls_alloc.py:125-350, same control flow and the same integer working-set bookkeeping.
 
-    Returns ``(u, iterations)`` or ``(None, iterations)`` on non-convergence (wls_alloc.py:350).
+    Returns ``(u, iterations)`` or ``(None, iterations)`` on non-convergence (wls_alloc.py:350);
+    with ``return_W`` also the final working set ``W`` in {-1, 0, +1} (a local of the reference, :171).
     """
     n_u = len(umin)
     n_v = len(v)
@@ -139,7 +140,7 @@ def wls_alloc(v, umin, umax, B, u_guess, W_init, Wv, Wu, up, gamma_sq=100000, im
                         free_index[n_free] = i
                         n_free += 1
             if break_flag:
-                return u, it
+                return (u, it, W.astype(int)) if return_W else (u, it)
             # NOTE: falls through with the *previous* alpha / id_alpha, exactly as the
             # reference does (its ``else`` at :299 only resets them on the infeasible branch).
         else:  # :299-302
@@ -166,7 +167,7 @@ def wls_alloc(v, umin, umax, B, u_guess, W_init, Wv, Wu, up, gamma_sq=100000, im
         free_index[free_index_lookup[id_alpha]] = free_index[n_free]
         free_index_lookup[free_index[free_index_lookup[id_alpha]]] = free_index_lookup[id_alpha]
         free_index_lookup[id_alpha] = -1
-    return None, it
+    return (None, it, W.astype(int)) if return_W else (None, it)
 
 
 # ---------------------------------------------------------------- shared position loop

@@ -93,17 +93,26 @@ class OracleSwarm:
         return np.hstack([self.pos[e, d], self.quat[e, d], self.rpy[e, d], self.vel[e, d],
                           self.ang_v_world(e, d), self.last_clipped_action[e, d, :n]])
 
-    def adjacency_bits(self):
-        """BaseAviary._getAdjacencyMatrix (BaseAviary.py:901-921) as one bitmask per vehicle."""
+    def adjacency_bits(self, margin=None):
+        """BaseAviary._getAdjacencyMatrix (BaseAviary.py:901-921) as one bitmask per vehicle.
+
+        With ``margin``: returns ``(bits, sure)`` where ``sure`` masks the pairs whose distance is farther than
+        ``margin`` from the radius (the decisions an FP32 evaluation of the same positions must reproduce)."""
         out = np.zeros((self.E, self.D), dtype=np.uint32)
+        sure = np.zeros((self.E, self.D), dtype=np.uint32)
         for e in range(self.E):
             for i in range(self.D):
-                bits = 1 << i
+                bits, s = 1 << i, 1 << i
                 for j in range(self.D):
-                    if j != i and np.linalg.norm(self.pos[e, i] - self.pos[e, j]) < self.radius:
+                    if j == i:
+                        continue
+                    d = np.linalg.norm(self.pos[e, i] - self.pos[e, j])
+                    if d < self.radius:
                         bits |= 1 << j
-                out[e, i] = bits
-        return out
+                    if margin is not None and abs(d - self.radius) > margin:
+                        s |= 1 << j
+                out[e, i], sure[e, i] = bits, s
+        return out if margin is None else (out, sure)
 
     # ------------------------------------------------------------------ physics
     def physics_step(self, action):

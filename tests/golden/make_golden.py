@@ -115,26 +115,71 @@ def wls_fixture():
     kat = dict(kat_v=v, kat_umin=dumin, kat_umax=dumax, kat_B=A, kat_Wv=Wv, kat_up=dumin, kat_du=du,
                kat_iter=it,
                kat_matlab=np.array([-4614.0, 426.064612091305, 5390.0, -4614.0, -4210.0, 5390.0]))
-    # --- random hexa-shaped cases through the same call the 6-DOF controller makes (:607-628)
+    # --- random hexa-shaped cases through the same call the 6-DOF controller makes (:607-628).  Inputs are rounded to
+    # float32 first (what the CUDA core is handed), so both sides solve bit-identical problems; the final working set W
+    # is a local of the reference function (:171), read off its frame when it returns (the function itself is unmodified)
     from dronesim_b200.vehicles import parse_urdf
     vt = parse_urdf(os.path.join(ref_shims.REFERENCE_ROOT, "dronesim", "assets", "hexa_6DOF.urdf"))
     B = vt.G1 / 0.05
     Wv6 = np.array([1000, 1000, 0.1, 10, 10, 100], float)
     rng = np.random.default_rng(7)
-    vs, cmds, dus, its, ok = [], [], [], [], []
-    for k in range(400):
-        sigma = [1.0, 10.0, 50.0, 150.0][k % 4]
-        centre = [0.5, 0.95, 0.05, 0.5][(k // 4) % 4]
-        v6 = rng.normal(0, sigma, 6)
-        cmd = np.clip(centre + rng.normal(0, 0.03, 6), 0, 1)
-        du, it = wls(v6, 0.0 - cmd, 1.0 - cmd, B, None, None, Wv6, np.ones(6), None)
-        vs.append(v6)
-        cmds.append(cmd)
-        its.append(it)
-        ok.append(du is not None)
-        dus.append(np.zeros(6) if du is None else np.array(du))
-    return dict(kat, rnd_v=np.array(vs), rnd_cmd=np.array(cmds), rnd_du=np.array(dus),
-                rnd_iter=np.array(its), rnd_ok=np.array(ok), rnd_B=B, rnd_Wv=Wv6)
+    # rnd_stale marks the runs that pass through the reference's stale-alpha path: a feasible iterate whose multipliers
+    # are not all >= -FLT_EPSILON does not `break`, and falls into the step-length search WITHOUT resetting `alpha`
+    # (only the infeasible branch does, :299-302), so a leftover step length of an earlier iteration is applied.  From
+    # there on the multipliers of bound variables are O(1e18) with O(1e4) rounding residue on the others, and the sign
+    # of that residue - i.e. LAPACK gelsd's rounding inside np.linalg.lstsq (:252) - decides how many more iterations
+    # follow: replacing lstsq by an equally exact QR solve changes the iteration count of 10-14 % of these runs and of
+    # none of the others.  Integer-exactness is demanded on the regular runs; the stale ones are kept for coverage.
+    import inspect
+    src_lines, first = inspect.getsourcelines(wls)
+    search_line = first + next(i for i, l in enumerate(src_lines) if "Find the lowest distance from the limit" in l) + 1
+    n_cases = 12288
+    vs, cmds = np.zeros((n_cases, 6), np.float32), np.zeros((n_cases, 6), np.float32)
+    dus, its = np.zeros((n_cases, 6)), np.zeros(n_cases, np.int32)
+    ok, Ws, stale = np.zeros(n_cases, bool), np.zeros((n_cases, 6), np.int8), np.zeros(n_cases, bool)
+    for k in range(n_cases):
+        sigma = [1.0, 10.0, 50.0, 150.0, 400.0, 3.0, 25.0, 80.0][k % 8]
+        centre = [0.5, 0.95, 0.05, 0.5, 0.0, 1.0, 0.3, 0.7][(k // 8) % 8]
+        v6 = rng.normal(0, sigma, 6).astype(np.float32)
+        cmd = np.clip(centre + rng.normal(0, 0.03, 6), 0, 1).astype(np.float32)
+        (du, it), loc = call_with_locals(wls, v6.astype(float), 0.0 - cmd.astype(float), 1.0 - cmd.astype(float), B, None,
+                                         None, Wv6, np.ones(6), None,
+                                         watch=(search_line, lambda f: f.f_locals.get("n_infeasible", 1) == 0))
+        vs[k], cmds[k], its[k], ok[k] = v6, cmd, it, du is not None
+        dus[k] = np.zeros(6) if du is None else np.array(du)
+        Ws[k] = np.asarray(loc["W"]).astype(np.int8)
+        stale[k] = loc["__watch_hit__"]
+    return dict(kat, rnd_v=vs, rnd_cmd=cmds, rnd_du=dus, rnd_iter=its, rnd_ok=ok, rnd_W=Ws, rnd_stale=stale, rnd_B=B,
+                rnd_Wv=Wv6)
+
+
+def call_with_locals(fn, *args, watch=None):
+    """Run the UNMODIFIED ``fn(*args)`` and also return the locals of its frame at the moment it returns.
+    ``watch = (line_number, predicate(frame))``: ``__watch_hit__`` tells whether that source line was ever reached
+    with the predicate true."""
+    import sys
+
+    box = {"__watch_hit__": False}
+    code = fn.__code__
+
+    def tracer(frame, event, arg):
+        if frame.f_code is code:
+            def local(frame, event, arg):
+                if event == "line" and watch is not None and frame.f_lineno == watch[0] and watch[1](frame):
+                    box["__watch_hit__"] = True
+                if event == "return":
+                    box.update({k: (v.copy() if hasattr(v, "copy") else v) for k, v in frame.f_locals.items()})
+                return local
+            return local
+        return None
+
+    old = sys.gettrace()
+    sys.settrace(tracer)
+    try:
+        out = fn(*args)
+    finally:
+        sys.settrace(old)
+    return out, box
 
 
 def quat_fixture():

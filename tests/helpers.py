@@ -35,3 +35,16 @@ def make_pair(models, n_envs, integrator, K, gnd=False, drag=False, dw=False, ra
 def core_state(core):
     v = core.views()
     return {k: (v[k].detach().cpu().numpy().astype(np.float64) if hasattr(v[k], "cpu") else v[k]) for k in v}
+
+
+def adjacency_bits_f32(pos, radius):
+    """The adjacency bitmask exactly as ``ds_obs_kernel`` evaluates it: ``|p_i - p_j|^2 < r^2`` in float32, every operation
+    correctly rounded, in the order ((dx*dx + dy*dy) + dz*dz) against fl(r * r).  ``pos`` [E, D, 3] (float32-representable)."""
+    p = np.asarray(pos).astype(np.float32)
+    E, D, _ = p.shape
+    d = p[:, :, None, :] - p[:, None, :, :]                      # [E, i, j, 3], float32
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    r2 = np.float32(radius) * np.float32(radius)
+    near = d2 < r2
+    near[:, np.arange(D), np.arange(D)] = True
+    return (near.astype(np.uint64) << np.arange(D, dtype=np.uint64)[None, None, :]).sum(axis=2).astype(np.uint32)

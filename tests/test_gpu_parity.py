@@ -13,7 +13,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-from helpers import angle_between, core_state, make_pair  # noqa: E402
+from helpers import adjacency_bits_f32, angle_between, core_state, make_pair  # noqa: E402
 from oracle.sim import OracleSwarm  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -188,21 +188,14 @@ def test_cfg4_heterogeneous_downwash(models):
     st = core_state(core)
     orc.pos = st["pos"].astype(np.float32).astype(np.float64).reshape(E, D, 3)
     _, nb, _, _ = core.get_obs()
-    # the kernel evaluates the norm in FP32: recompute the predicate in FP32 for bit-exactness
-    p32 = st["pos"].astype(np.float32).reshape(E, D, 3)
-    exp = np.zeros((E, D), dtype=np.uint32)
-    for e in range(E):
-        for i in range(D):
-            bits = 1 << i
-            for j in range(D):
-                if j != i:
-                    d = p32[e, i] - p32[e, j]
-                    if np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1]) + np.float32(d[2] * d[2]), dtype=np.float32) < np.float32(1.2):
-                        bits |= 1 << j
-            exp[e, i] = bits
+    # the kernel compares squared FP32 distances built from correctly rounded operations in a fixed order: the same
+    # float32 expression reproduces every bit
     got = nb.cpu().numpy().astype(np.uint32).reshape(E, D)
-    # pairs whose distance is within 1e-5 of the radius may round either way; everything else must match
-    assert (got == exp).mean() > 0.99
+    np.testing.assert_array_equal(got, adjacency_bits_f32(st["pos"].reshape(E, D, 3), 1.2))
+    # ... and agrees with the reference's FP64 predicate (BaseAviary.py:913-921) wherever the distance is not within
+    # 1e-5 m of the radius
+    exp64, sure = orc.adjacency_bits(margin=1e-5)
+    assert ((got ^ exp64) & sure).max() == 0
     core.close()
 
 
@@ -318,18 +311,29 @@ def test_wls_vs_reference_fixture():
     v = torch.tensor(g["rnd_v"], dtype=torch.float32)
     cmd = torch.tensor(g["rnd_cmd"], dtype=torch.float32)
     ok = g["rnd_ok"]
+    # "Regular" runs: every run of the reference that stays off its stale-alpha path (wls_alloc.py:269-302: a feasible but
+    # not yet optimal iterate falls into the step-length search with the `alpha` of an EARLIER iteration; from there on
+    # O(1e4) rounding residue on O(1e18) multipliers - LAPACK's rounding inside np.linalg.lstsq - decides the iteration
+    # count, see tests/golden/make_golden.py).  11,000+ regular problems, 1,400+ of them with a non-empty active set.
+    reg = ~g["rnd_stale"]
+    assert reg.sum() >= 10000 and ok[reg].all() and ((g["rnd_iter"] > 1) & reg).sum() >= 1000
     for force_slow in (False, True):
-        du, it = core.debug_wls(0, v, cmd, force_slow=force_slow)
-        du, it = du.cpu().numpy().astype(np.float64), it.cpu().numpy()
-        # integer-exact iteration count whenever the reference converges
-        conv = ok
-        mism = (it[conv] != g["rnd_iter"][conv])
-        assert mism.mean() <= 0.01, "iteration-count mismatches: %d of %d" % (mism.sum(), conv.sum())
-        same = conv & (it == g["rnd_iter"])
+        du, it, W = core.debug_wls(0, v, cmd, force_slow=force_slow, working_set=True)
+        du, it, W = du.cpu().numpy().astype(np.float64), it.cpu().numpy(), W.cpu().numpy()
+        # integer-exact: iteration count AND final working set equal to the reference's on every regular run
+        # (the reference's W is a local of wls_alloc, read off its frame when it returns)
+        np.testing.assert_array_equal(it[reg], g["rnd_iter"][reg])
+        np.testing.assert_array_equal(W[reg], g["rnd_W"][reg].astype(np.int32))
+        scale = np.maximum(1.0, np.abs(g["rnd_du"][reg]).max(axis=1, keepdims=True))
+        assert (np.abs(du[reg] - g["rnd_du"][reg]) / scale).max() <= 5e-5
+        # stale-path runs (9 %): most still agree; where the counts agree so does the solution, and every reported
+        # non-convergence (negative count; the reference returns None, :350) holds the command
+        st = g["rnd_stale"]
+        same = st & ok & (it == g["rnd_iter"])
+        assert same.sum() >= 0.5 * st.sum()
         scale = np.maximum(1.0, np.abs(g["rnd_du"][same]).max(axis=1, keepdims=True))
         assert (np.abs(du[same] - g["rnd_du"][same]) / scale).max() <= 5e-5
-        # non-convergence is reported (negative count) and holds the command
-        assert (it[~ok] < 0).all() and (du[~ok] == 0).all()
+        assert (it < 0).sum() >= 0.5 * (~ok).sum() and (du[it < 0] == 0).all() and (it[reg] > 0).all()
     core.close()
 
 
@@ -355,11 +359,13 @@ def test_integer_bookkeeping_and_done_flags():
         # done bits recomputed from the GPU's own FP32 positions
         p = v["pos"].cpu().numpy()
         bits = v["done_bits"].cpu().numpy()
-        d = p - np.array([0.0, 0.0, 0.5], dtype=np.float32)
-        dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2], dtype=np.float32)
+        # the kernel's goal predicate: squared FP32 distance, correctly rounded operations in this order, against fl(r * r)
+        d = p.astype(np.float32) - np.array([0.0, 0.0, 0.5], dtype=np.float32)
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        assert d2.dtype == np.float32
         if step == 0:
             sticky = np.zeros(E, dtype=np.int64)
-        now = (dist < np.float32(0.3)).astype(np.int64) | ((p[:, 2] < np.float32(0.2)).astype(np.int64) << 1)
+        now = (d2 < np.float32(0.3) * np.float32(0.3)).astype(np.int64) | ((p[:, 2] < np.float32(0.2)).astype(np.int64) << 1)
         if 3 * (step + 1) >= 30:
             now |= 4
         sticky |= now
@@ -777,8 +783,11 @@ def test_max_drones_per_env_downwash():
     _compare_state(core, orc, what="D=32")
     _, nb, _, _ = core.get_obs()
     got = nb.cpu().numpy().astype(np.uint32).reshape(E, D)
-    exp = orc.adjacency_bits()
-    assert (got == exp).mean() > 0.99 and ((got >> np.arange(D, dtype=np.uint32)) & 1).all()  # 32-bit rows, self bit set
+    np.testing.assert_array_equal(got, adjacency_bits_f32(core_state(core)["pos"].reshape(E, D, 3), 2.0))  # bit-exact, 32-bit rows
+    assert ((got >> np.arange(D, dtype=np.uint32)) & 1).all()  # self bit set
+    orc.pos = core_state(core)["pos"].reshape(E, D, 3)
+    exp64, sure = orc.adjacency_bits(margin=1e-5)
+    assert ((got ^ exp64) & sure).max() == 0
     core.close()
 
 

@@ -25,11 +25,17 @@ def test_wls_known_answer_matlab():
 def test_wls_random_cases_iterations_and_active_set():
     g = np.load(os.path.join(GOLD, "wls_cases.npz"))
     B, Wv = g["rnd_B"], g["rnd_Wv"]
-    for k in range(g["rnd_v"].shape[0]):
-        cmd = g["rnd_cmd"][k]
-        du, it = oc.wls_alloc(g["rnd_v"][k], 0.0 - cmd, 1.0 - cmd, B, None, None, Wv, np.ones(6), None)
+    # the oracle is a pure-Python loop: every 5th of the 10,240 reference cases, plus every non-converging one (whose 100
+    # iterations dominate the time: keep 12 of them)
+    idx = sorted(set(range(0, g["rnd_v"].shape[0], 5)) | set(np.flatnonzero(~g["rnd_ok"])[:12].tolist()))
+    idx = [k for k in idx if g["rnd_ok"][k] or k in set(np.flatnonzero(~g["rnd_ok"])[:12].tolist())]
+    for k in idx:
+        cmd = g["rnd_cmd"][k].astype(float)
+        du, it, W = oc.wls_alloc(g["rnd_v"][k].astype(float), 0.0 - cmd, 1.0 - cmd, B, None, None, Wv, np.ones(6), None,
+                                 return_W=True)
         assert it == g["rnd_iter"][k]
         assert (du is not None) == bool(g["rnd_ok"][k])
+        np.testing.assert_array_equal(W, g["rnd_W"][k])  # the working set, read off the reference function's frame
         if du is not None:
             np.testing.assert_allclose(du, g["rnd_du"][k], rtol=1e-9, atol=1e-9)
     assert (~g["rnd_ok"]).sum() >= 1  # the fixture exercises the reference's None return (wls_alloc.py:350)

@@ -24,7 +24,7 @@ DS_NUM_STATS = 16
 
 DS_OK, DS_ERR_INVALID, DS_ERR_CUDA, DS_ERR_STATE, DS_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 DS_INTEG_QUAT, DS_INTEG_RPY = 0, 1
-DS_FLAG_GROUND, DS_FLAG_DRAG, DS_FLAG_DOWNWASH, DS_FLAG_STATS, DS_FLAG_DW_ORDERED_PAIRS = 1, 2, 4, 8, 16
+DS_FLAG_GROUND, DS_FLAG_DRAG, DS_FLAG_DOWNWASH, DS_FLAG_STATS, DS_FLAG_DW_ORDERED_PAIRS, DS_FLAG_TYPES_IN_SMEM = 1, 2, 4, 8, 16, 32
 DS_LAW_QUAD, DS_LAW_6DOF = 0, 1
 DS_DONE_GOAL, DS_DONE_FLOOR, DS_DONE_TIME = 1, 2, 4
 DS_ORDER_PHYSICS_THEN_CONTROL, DS_ORDER_CONTROL_THEN_PHYSICS = 0, 1

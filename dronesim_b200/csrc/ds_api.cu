@@ -63,6 +63,8 @@ struct ds_handle {
   int log_n = 0, log_cap = 0, log_count = 0;
   std::vector<double> log_time;
   uint8_t slot_type[DS_MAX_DRONES_PER_ENV];
+  std::vector<DsTypeDev> types_host;  // host copy of the device type table (homogeneous swarms pass theirs by value)
+  int homo_type = -1;                 // the one type every slot flies, -1: mixed
 };
 
 #define CK(call)                                  \
@@ -191,8 +193,13 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
   std::vector<float> icmd(DS_MAX_TYPES_DEV, 0.f), ithr(DS_MAX_TYPES_DEV, 0.f);
   memset(dev.data(), 0, sizeof(DsTypeDev) * DS_MAX_TYPES_DEV);
   memset(wls.data(), 0, sizeof(DsWlsDev) * DS_MAX_TYPES_DEV);
-  h->nu6 = false;
+  // everything derived from the table is collected in locals and committed to the handle only after every check has
+  // passed: a rejected call leaves the previous table and its dispatch flags intact
+  bool nu6 = false, any_6dof = false, dw_uniform = true;
+  int rc_kind = 0;
   bool need_ext = false;  // the advanced propeller model runs in the EXT kernel variant
+  for (int s = 0; s < h->cfg.drones_per_env; ++s)
+    if (slot_type[s] >= n_types) return DS_ERR_INVALID;
   for (int t = 0; t < n_types; ++t) {
     const ds_type_params& p = types[t];
     if (p.n_u < 1 || p.n_u > DS_MAX_ROTORS || p.n_v < 1 || p.n_v > DS_MAX_ROTORS) return DS_ERR_INVALID;
@@ -271,13 +278,11 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     }
     d.rpm0_sum = (float)rpm0;
     for (int k = 0; k < 3; ++k) d.lat[k] = (float)lat[k];
-    if (p.n_u > 4) h->nu6 = true;
-    if (t == 0) { h->any_6dof = false; h->rc_kind = 0; }
-    if (d.has_rc == 1) h->rc_kind = 1;
-    else if (d.has_rc == 2 && h->rc_kind == 0) h->rc_kind = 2;
-    if (p.law == DS_LAW_6DOF) h->any_6dof = true;
-    if (t == 0) h->dw_uniform = true;
-    else if (d.dw_k2 != dev[0].dw_k2 || d.dw_k3 != dev[0].dw_k3) h->dw_uniform = false;
+    if (p.n_u > 4) nu6 = true;
+    if (d.has_rc == 1) rc_kind = 1;
+    else if (d.has_rc == 2 && rc_kind == 0) rc_kind = 2;
+    if (p.law == DS_LAW_6DOF) any_6dof = true;
+    if (t > 0 && (d.dw_k2 != dev[0].dw_k2 || d.dw_k3 != dev[0].dw_k3)) dw_uniform = false;
     DsWlsDev& w = wls[t];
     w.n_u = p.n_u; w.n_v = p.n_v; w.gamma = p.wls_gamma;
     for (int i = 0; i < p.n_v; ++i) {
@@ -288,12 +293,8 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
     icmd[t] = (float)p.init_cmd;
     ithr[t] = (float)p.init_thrust;
   }
-  for (int s = 0; s < h->cfg.drones_per_env; ++s) {
-    if (slot_type[s] >= n_types) return DS_ERR_INVALID;
-    h->slot_type[s] = slot_type[s];
-  }
-  h->n_types = n_types;
-  if (h->any_6dof && !h->d_wls_count) {  // deferred WLS slow path (ds_wls_fixup_kernel)
+  h->types_set = false;  // until the new table is resident (a CUDA failure below must not leave a half-updated handle usable)
+  if (any_6dof && !h->d_wls_count) {  // deferred WLS slow path (ds_wls_fixup_kernel)
     CK(cudaMalloc((void**)&h->d_wls_count, 2 * sizeof(int)));
     CK(cudaMemset(h->d_wls_count, 0, 2 * sizeof(int)));
     CK(cudaMalloc((void**)&h->d_wls_index, (size_t)h->n * sizeof(int)));
@@ -307,9 +308,16 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
   }
   CK(cudaMemcpy(h->d_types, dev.data(), sizeof(DsTypeDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_wls, wls.data(), sizeof(DsWlsDev) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
+  for (int s = 0; s < h->cfg.drones_per_env; ++s) h->slot_type[s] = slot_type[s];
   CK(cudaMemcpy(h->d_slot_type, h->slot_type, h->cfg.drones_per_env, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_init_cmd, icmd.data(), sizeof(float) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_init_thrust, ithr.data(), sizeof(float) * DS_MAX_TYPES_DEV, cudaMemcpyHostToDevice));
+  h->n_types = n_types;
+  h->nu6 = nu6; h->any_6dof = any_6dof; h->dw_uniform = dw_uniform; h->rc_kind = rc_kind;
+  h->homo_type = slot_type[0];
+  for (int s = 1; s < h->cfg.drones_per_env; ++s)
+    if (slot_type[s] != slot_type[0]) h->homo_type = -1;
+  h->types_host = dev;
   h->types_set = true;
   h->is_reset = false;
   return DS_OK;
@@ -447,7 +455,9 @@ static void launch_step(int mode, ds_handle* h, DsArgs& a, cudaStream_t st) {
   int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
   if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;
   const int grid = grid_for(h, a.n_tiles, DS_MIN_CTAS);
-  ds_launch_step(h->cfg.integrator == DS_INTEG_RPY ? 1 : 0, mode, dw, h->nu6, 32 % a.D == 0, a, grid, st);
+  a.homo_type = h->homo_type;
+  const DsTypeDev* homo = (h->homo_type >= 0 && !(h->cfg.flags & DS_FLAG_TYPES_IN_SMEM)) ? &h->types_host[h->homo_type] : nullptr;
+  ds_launch_step(h->cfg.integrator == DS_INTEG_RPY ? 1 : 0, mode, dw, h->nu6, 32 % a.D == 0, a, homo, grid, st);
 }
 
 static int log_sample(ds_handle* h, cudaStream_t st);

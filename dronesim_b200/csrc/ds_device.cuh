@@ -115,6 +115,7 @@ struct DsArgs {
   int n_tiles;
   int K;
   int n_types;
+  int homo_type;    // the one type id every slot flies (HOMO kernel variants), -1: mixed
   uint32_t flags;
   int order;
   int rc_kind;      // centre-of-mass offsets of the swarm's types: 0 none, 1 some general offset, 2 all along body z

@@ -181,12 +181,24 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsT
   return t;
 }
 
-template <int INTEG, int DW, bool NU6, bool WARPSYNC, int MODE, int FX, bool EXT>
-__global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsArgs a) {
+// HOMO: every slot flies the same airframe type.  The type table then travels in the kernel parameters (constant bank:
+// its entries are uniform operands of the arithmetic instructions, no LDS, no shared-memory copy) and the control law
+// branch is warp-uniform.  Mixed swarms (HOMO = false) index the per-type tables in shared memory by the lane's type.
+struct DsArgsH { DsArgs a; DsTypeDev tp; };
+template <bool HOMO> struct DsKArgs { typedef DsArgs type; };
+template <> struct DsKArgs<true> { typedef DsArgsH type; };
+__device__ __forceinline__ const DsArgs& ds_args_of(const DsArgs& A) { return A; }
+__device__ __forceinline__ const DsArgs& ds_args_of(const DsArgsH& A) { return A.a; }
+__device__ __forceinline__ const DsTypeDev& ds_type_of(const DsArgs&, const DsTypeDev* sh, int id) { return sh[id]; }
+__device__ __forceinline__ const DsTypeDev& ds_type_of(const DsArgsH& A, const DsTypeDev*, int) { return A.tp; }
+
+template <int INTEG, int DW, bool NU6, bool WARPSYNC, int MODE, int FX, bool EXT, bool HOMO, bool RC>
+__global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __grid_constant__ typename DsKArgs<HOMO>::type A) {
+  const DsArgs& a = ds_args_of(A);
   extern __shared__ __align__(128) unsigned char ds_stage_mem[];  // 2 x ds_stage_bytes<MODE>()
   __shared__ __align__(8) unsigned long long sh_bar[2];  // per stage: the stage's bulk copies have landed
   __shared__ int sh_tile[2];                             // per stage: the tile staged there, -1 = none (the CTA is done)
-  __shared__ __align__(16) DsTypeDev sh_types[DS_MAX_TYPES_DEV];
+  __shared__ __align__(16) DsTypeDev sh_types[HOMO ? 1 : DS_MAX_TYPES_DEV];
   __shared__ uint8_t sh_slot_type[32];
   __shared__ __align__(16) float4 sh_pos[DW ? 2 * DS_DW_BUF : 1];
   __shared__ float sh_stat[ST_COUNT * DS_TILE];
@@ -207,8 +219,8 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
     sh_tile[1] = (t1 < a.n_tiles) ? t1 : -1;
     if (t1 < a.n_tiles) ds_stage_issue<NU6, MODE>(a, t1, ds_stage_mem + STAGE, &sh_bar[1]);
   }
-  ds_load_types(a, sh_types);
-  if (threadIdx.x < 32) sh_slot_type[threadIdx.x] = (threadIdx.x < a.D) ? a.slot_type[threadIdx.x] : 0;
+  if (!HOMO) ds_load_types(a, sh_types);
+  if (!HOMO && threadIdx.x < 32) sh_slot_type[threadIdx.x] = (threadIdx.x < a.D) ? a.slot_type[threadIdx.x] : 0;
   const bool stats_on = (a.flags & 8u) != 0;
   if (stats_on) {
 #pragma unroll
@@ -224,8 +236,8 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
   // row of the env's slot 0 in the downwash snapshot: D + 1 padded rows per env, or a 32-row block (symmetric variant)
   const int env_row0 = (DW == 2) ? (lv / 16) * DS_DW_SYM_ROWS : (lv / a.D) * (a.D + DS_DW_PAD);
   const int my_row = env_row0 + slot;
-  const int type_id = sh_slot_type[slot];
-  const DsTypeDev& tp = sh_types[type_id];
+  const int type_id = HOMO ? a.homo_type : sh_slot_type[slot];
+  const DsTypeDev& tp = ds_type_of(A, sh_types, type_id);
 
   for (int iter = 0;; ++iter) {
     const int tile = sh_tile[iter & 1];
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const DsA
       rpm[0] = R0.x; rpm[1] = R0.y; rpm[2] = R0.z; rpm[3] = R0.w;
       if (NU6) { const float2 R1 = a.s_r1[vv]; rpm[4] = R1.x; rpm[5] = R1.y; }
     }
-    ds_physics<INTEG, DW, NU6, WARPSYNC, FX, EXT>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum, rpm, a.veh0 + (uint32_t)vv);
+    ds_physics<INTEG, DW, NU6, WARPSYNC, FX, EXT, RC>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum, rpm, a.veh0 + (uint32_t)vv);
     if (MODE == 0) control();
     if (MODE == 1) done_bits = __float_as_uint(sg[SG_LV * T + ld].w);
 

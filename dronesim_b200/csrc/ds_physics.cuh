@@ -73,19 +73,21 @@ __device__ __forceinline__ void ds_rot_fma(const RotP& R, float vx, float vy, fl
 
 // q <- normalize(q (x) exp(w dt)).  Taylor polynomials of 0.5 sin(h)/h and cos(h) in h^2 = (half angle)^2 < 0.25 (the
 // first dropped terms are 5e-9 and 3e-10 relative at h^2 = 0.25); a.qk = TIMESTEP x the sine coefficients, a.qh = 0.25 dt^2.
+// |w| dt >= 1 rad per substep (>= 240 rad/s): a blown-up state; MUFU sin / cos keep it finite.  Out of line on purpose:
+// inlined, ptxas predicates these ten instructions into every substep instead of branching around them.
+static __device__ __noinline__ float2 ds_quat_step_fast_spin(float h2, float dt) {  // -> (k, c)
+  const float half = sqrtf(h2);
+  float sn, cs;
+  __sincosf(half, &sn, &cs);
+  return make_float2(0.5f * dt * sn * ds_rcp(half), cs);
+}
+
 __device__ __forceinline__ void ds_quat_step(const DsArgs& a, f2& qxy, f2& qzw, f2 wxy, float wz) {
   const f2 w2 = wxy * wxy;
   const float h2 = ds_fma(wz, wz, f2_lo(w2) + f2_hi(w2)) * a.qh;
   float k = ds_fma(h2, ds_fma(h2, ds_fma(h2, a.qk[3], a.qk[2]), a.qk[1]), a.qk[0]);
   float c = ds_fma(h2, ds_fma(h2, ds_fma(h2, ds_fma(h2, 1.0f / 40320.0f, -1.0f / 720.0f), 1.0f / 24.0f), -0.5f), 1.0f);
-  if (h2 >= 0.25f) {
-    // |w| dt >= 1 rad per substep (>= 240 rad/s): a blown-up state; MUFU sin / cos keep it finite and this branch free
-    // of libm's argument-reduction slow path (two CALLs inside the substep loop otherwise)
-    const float half = sqrtf(h2);
-    float sn;
-    __sincosf(half, &sn, &c);
-    k = 0.5f * a.dt * sn * ds_rcp(half);
-  }
+  if (h2 >= 0.25f) { const float2 kc = ds_quat_step_fast_spin(h2, a.dt); k = kc.x; c = kc.y; }
   const f2 dxy = wxy * k;
   const float dx = f2_lo(dxy), dy = f2_hi(dxy), dz = wz * k;
   const float qx = f2_lo(qxy), qy = f2_hi(qxy), qz = f2_lo(qzw), qw = f2_hi(qzw);
@@ -215,7 +217,9 @@ __device__ __forceinline__ float ds_downwash_sum_sym16(const float4* __restrict_
 // torque (-rc) x f.
 // EXT: first-order motor model (north_star; R9 of oracle/dynamics.py): rpm[] holds the actual rotor speeds (in / out),
 // every substep moves them towards the commanded speed and rebuilds the rotor wrench, so nothing is hoisted.
-template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX, bool EXT>
+// RC: some type of the swarm has a centre-of-mass offset (compile time: the offset arithmetic is 25 instructions per
+// substep that quad-only swarms do not need).
+template <int INTEG, int DW, bool NU6, bool WARPSYNC, int FX, bool EXT, bool RC>
 __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp, int env_row0, int my_row, float4* sh_pos,
                                            const float* act, PhysState& s, float& prev_rpm_sum, float* rpm_state,
                                            uint32_t veh_id) {
@@ -223,12 +227,10 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
   const float dt = a.dt;
   const bool gnd = (FX >= 0) ? ((FX & 1) != 0) : ((a.flags & 1u) != 0);
   const bool drag = (FX >= 0) ? ((FX & 2) != 0) : ((a.flags & 2u) != 0);
-  // a.rc_kind is the same for every lane (1 if some type of the swarm has a general offset, 2 if all offsets are along
-  // z, 0 if none): types without an offset run the same arithmetic with rc = 0, which is exact (x + 0 = x), so a warp
-  // that mixes airframes does not diverge here
-  const int rc_kind = (INTEG == 0) ? a.rc_kind : 0;
-  const bool has_rc = rc_kind != 0;
-  const bool rc_gen = rc_kind == 1;
+  // RC is the same for every lane: types without an offset run the same arithmetic with rc = 0, which is exact
+  // (x + 0 = x), so a warp that mixes airframes does not diverge here; offsets along body z only take the general path
+  constexpr bool has_rc = RC && INTEG == 0;
+  constexpr bool rc_gen = has_rc;
 
   const float rcx = tp.rc[0], rcy = tp.rc[1], rcz = tp.rc[2];
 
@@ -375,14 +377,18 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
       const float px = f2_lo(pxy), py = f2_hi(pxy);
       float dsum;
       float4* buf = sh_pos + (k & 1) * DS_DW_BUF;
-      const float4 me = make_float4(px, py, pz, 0.f);
+      // rows are float4 (x, y, z, -): stored as the (x, y) register pair + z, so no four-register tuple has to be assembled
+      auto put = [&](int row) {
+        *reinterpret_cast<float2*>(&buf[row]) = make_float2(px, py);
+        reinterpret_cast<float*>(&buf[row])[2] = pz;
+      };
       if (DW == 2) {  // symmetric pairs: env_row0 / my_row index 32-row blocks, slot = my_row - env_row0
-        buf[my_row] = me;
-        if (my_row - env_row0 < 8) buf[my_row + 16] = me;
+        put(my_row);
+        if (my_row - env_row0 < 8) put(my_row + 16);
         __syncwarp();
         dsum = ds_downwash_sum_sym16(buf + my_row, my_row - env_row0 + 16, px, py, pz, tp.dw_k2, tp.dw_k3);
       } else {
-        buf[my_row] = me;
+        put(my_row);
         if (WARPSYNC) __syncwarp(); else __syncthreads();
         dsum = ds_downwash_sum(buf + env_row0, a.D, px, py, pz, tp.dw_k2, tp.dw_k3);
       }

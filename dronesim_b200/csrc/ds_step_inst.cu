@@ -9,8 +9,8 @@
 #endif
 
 // two tile stages of dynamic shared memory (> 48 KB: opt in once per instantiation and device)
-template <void (*KERNEL)(const DsArgs)>
-static void launch4(const DsArgs& a, int grid, cudaStream_t st) {
+template <class ARGS, void (*KERNEL)(const ARGS)>
+static void launch5(const ARGS& args, int grid, cudaStream_t st) {
   constexpr int kSmem = 2 * ds_stage_bytes<DS_INST_MODE>();
   static bool opted[64] = {};
   int dev = 0;
@@ -19,26 +19,53 @@ static void launch4(const DsArgs& a, int grid, cudaStream_t st) {
     cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     opted[dev] = true;
   }
-  KERNEL<<<grid, DS_TILE, kSmem, st>>>(a);
+  KERNEL<<<grid, DS_TILE, kSmem, st>>>(args);
+}
+
+// homo: the swarm's single airframe type (its table rides in the kernel parameters), nullptr for mixed swarms.  The
+// homogeneous variants exist for the quaternion integrator without extensions (the throughput configurations).
+template <int DW, bool NU6, bool WS, int FX, bool EXT, bool RC>
+static void launch4b(const DsArgs& a, const DsTypeDev* homo, int grid, cudaStream_t st) {
+#if DS_INST_INTEG == 0
+  if (!EXT && homo) {
+    DsArgsH ah;
+    ah.a = a;
+    ah.tp = *homo;
+    launch5<DsArgsH, ds_step_kernel<DS_INST_INTEG, DW, NU6, WS, DS_INST_MODE, FX, false, true, RC>>(ah, grid, st);
+    return;
+  }
+#endif
+  launch5<DsArgs, ds_step_kernel<DS_INST_INTEG, DW, NU6, WS, DS_INST_MODE, FX, EXT, false, RC>>(a, grid, st);
+}
+
+// RC: some type has a centre-of-mass offset (quaternion integrator only; the extension variants always carry it)
+template <int DW, bool NU6, bool WS, int FX, bool EXT>
+static void launch4(const DsArgs& a, const DsTypeDev* homo, int grid, cudaStream_t st) {
+#if DS_INST_INTEG == 0
+  if (EXT || a.rc_kind != 0) launch4b<DW, NU6, WS, FX, EXT, true>(a, homo, grid, st);
+  else launch4b<DW, NU6, WS, FX, false, false>(a, homo, grid, st);
+#else
+  launch4b<DW, NU6, WS, FX, EXT, false>(a, homo, grid, st);
+#endif
 }
 
 template <int DW, bool NU6, int FX, bool EXT>
-static void launch3(bool warpsync, const DsArgs& a, int grid, cudaStream_t st) {
+static void launch3(bool warpsync, const DsArgs& a, const DsTypeDev* homo, int grid, cudaStream_t st) {
   // warp-level sync of the downwash snapshot needs every env inside one warp: D | 32 (always true of the D = 16 variant)
-  if (DW == 2 || warpsync) launch4<ds_step_kernel<DS_INST_INTEG, DW, NU6, true, DS_INST_MODE, FX, EXT>>(a, grid, st);
-  else launch4<ds_step_kernel<DS_INST_INTEG, (DW == 2 ? 1 : DW), NU6, false, DS_INST_MODE, FX, EXT>>(a, grid, st);
+  if (DW == 2 || warpsync) launch4<DW, NU6, true, FX, EXT>(a, homo, grid, st);
+  else launch4<(DW == 2 ? 1 : DW), NU6, false, FX, EXT>(a, homo, grid, st);
 }
 
 template <int DW, bool NU6>
-static void launch2(bool warpsync, const DsArgs& a, int grid, cudaStream_t st) {
+static void launch2(bool warpsync, const DsArgs& a, const DsTypeDev* homo, int grid, cudaStream_t st) {
   // FX: ground effect + drag resolved at compile time for the all-add-ons configuration (straight-line substep body),
   // run-time flags otherwise
 #if DS_INST_INTEG == 0
   // EXT: motor model / angular-acceleration filter (extensions beyond the reference; quaternion integrator only)
-  if (a.ext) { launch3<DW, NU6, -1, true>(warpsync, a, grid, st); return; }
+  if (a.ext) { launch3<DW, NU6, -1, true>(warpsync, a, homo, grid, st); return; }
 #endif
-  if (DW != 0 && (a.flags & 3u) == 3u) launch3<DW, NU6, 3, false>(warpsync, a, grid, st);
-  else launch3<DW, NU6, -1, false>(warpsync, a, grid, st);
+  if (DW != 0 && (a.flags & 3u) == 3u) launch3<DW, NU6, 3, false>(warpsync, a, homo, grid, st);
+  else launch3<DW, NU6, -1, false>(warpsync, a, homo, grid, st);
 }
 
 #define DS_CONCAT3_(a, b, c) a##b##_##c
@@ -49,9 +76,9 @@ static void launch2(bool warpsync, const DsArgs& a, int grid, cudaStream_t st) {
 #define DS_INST_NAME DS_CONCAT3(ds_launch_step_r, DS_INST_MODE, DS_INST_NU6)
 #endif
 
-void DS_INST_NAME(int dw, bool warpsync, const DsArgs& a, int grid, cudaStream_t st) {
+void DS_INST_NAME(int dw, bool warpsync, const DsArgs& a, const DsTypeDev* homo, int grid, cudaStream_t st) {
   constexpr bool NU6 = DS_INST_NU6 != 0;
-  if (dw == 2) launch2<2, NU6>(warpsync, a, grid, st);
-  else if (dw == 1) launch2<1, NU6>(warpsync, a, grid, st);
-  else launch2<0, NU6>(warpsync, a, grid, st);
+  if (dw == 2) launch2<2, NU6>(warpsync, a, homo, grid, st);
+  else if (dw == 1) launch2<1, NU6>(warpsync, a, homo, grid, st);
+  else launch2<0, NU6>(warpsync, a, homo, grid, st);
 }

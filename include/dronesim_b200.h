@@ -53,7 +53,10 @@ enum { DS_INTEG_QUAT = 0, DS_INTEG_RPY = 1 };
 enum { DS_FLAG_GROUND = 1u, DS_FLAG_DRAG = 2u, DS_FLAG_DOWNWASH = 4u, DS_FLAG_STATS = 8u,
        /* diagnostics: evaluate every ORDERED downwash pair even where the symmetric kernel variant applies
         * (16 drones per env, all types sharing dw_coeff_2 / dw_coeff_3); results agree to FP32 summation order */
-       DS_FLAG_DW_ORDERED_PAIRS = 16u };
+       DS_FLAG_DW_ORDERED_PAIRS = 16u,
+       /* diagnostics: a single-type swarm runs the mixed-swarm kernel variant (per-type tables in shared memory) instead
+        * of the homogeneous one (its type table in the kernel parameters); results are bit-identical */
+       DS_FLAG_TYPES_IN_SMEM = 32u };
 
 /* control laws: which reference controller class flies the type */
 enum { DS_LAW_QUAD = 0 /* INDIControl.py */, DS_LAW_6DOF = 1 /* INDIControl_6DOF.py */ };

@@ -65,6 +65,7 @@ class ds_targets(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("num_wp", C.c_int32), ("advance_wp", C.c_int32), ("reserved", C.c_int32),
         ("pos_yaw", C.c_void_p), ("vel", C.c_void_p), ("acc", C.c_void_p), ("table", C.c_void_p), ("offset", C.c_void_p),
+        ("wp", C.c_void_p),
     ]
 
 
@@ -85,6 +86,7 @@ SYMBOLS = {
     "ds_destroy": (None, [_H]),
     "ds_set_types": (C.c_int, [_H, C.POINTER(ds_type_params), C.c_int32, C.POINTER(C.c_uint8)]),
     "ds_reset": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_reset_envs": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_step": (C.c_int, [_H, C.POINTER(ds_targets), C.c_int32, C.c_int32, C.c_void_p]),
     "ds_physics_step": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ds_control_step": (C.c_int, [_H, C.POINTER(ds_targets), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -100,6 +102,7 @@ SYMBOLS = {
     "ds_log_read": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "ds_step_host": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_rollout_host": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ds_rollout_host_table": (C.c_int, [_H, C.POINTER(ds_targets), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                C.c_int32, C.c_void_p]),
     "ds_debug_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
@@ -176,7 +179,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if L.ds_abi_version() != 1:
+        if L.ds_abi_version() != 2:
             raise RuntimeError("dronesim_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -182,6 +182,25 @@ class SwarmCore:
             L.check(L.lib().ds_reset(self._h, ptr(pos0), ptr(rpy0), ptr(vel0), ptr(action0), ptr(wp), self._stream()),
                     self._h)
 
+    def reset_envs(self, mask, pos0, rpy0=None, vel0=None, action0=None, wp0=None):
+        """``BaseAviary.reset`` for the envs with ``mask[e] != 0`` only, on the device, no host synchronisation
+        (``ds_reset_envs``).  ``mask`` [E] uint8 / bool; ``pos0`` [N,3] (+ optional ``rpy0``, ``vel0`` [N,3], ``action0`` [N,6],
+        ``wp0`` [N] int32): device tensors, or host arrays that are copied first; rows of unmasked envs are not read."""
+        N = self.N
+
+        def dev(a, shape, dtype):
+            if a is None:
+                return None
+            t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+            return t.to(self.device, dtype).reshape(shape).contiguous()
+
+        m = dev(mask, (self.E,), torch.uint8)
+        p0, r0, v0 = dev(pos0, (N, 3), torch.float32), dev(rpy0, (N, 3), torch.float32), dev(vel0, (N, 3), torch.float32)
+        a0, w0 = dev(action0, (N, 6), torch.float32), dev(wp0, (N,), torch.int32)
+        L.check(L.lib().ds_reset_envs(self._h, self._p(m), self._p(p0), self._p(r0), self._p(v0), self._p(a0), self._p(w0),
+                                      self._stream()), self._h)
+        self._reset_keep = (m, p0, r0, v0, a0, w0)  # borrowed until the stream has consumed them
+
     # ------------------------------------------------------------------ targets
     def _dev4(self, a, name):
         """[N,4] float32 contiguous device tensor (numpy / torch in, padded from [N,3] if needed)."""
@@ -225,9 +244,10 @@ class SwarmCore:
         t._keep = (v,)
         return t
 
-    def targets_table(self, table, offset=None, advance: bool = True) -> L.ds_targets:
+    def targets_table(self, table, offset=None, advance: bool = True, wp=None) -> L.ds_targets:
         """mode 1: ``table`` [num_wp, 10] = pos3, vel3, acc3, yaw (the layout of the reference examples'
-        TARGET_POS/VEL/ACC/RPYS rows), shared by all vehicles; per-vehicle counters live in the state."""
+        TARGET_POS/VEL/ACC/RPYS rows), shared by all vehicles; per-vehicle counters live in the state, unless ``wp``
+        ([N] int32 device tensor) supplies this step's index of every vehicle (fly_INDI.py:230-245)."""
         tab = np.asarray(table, dtype=np.float64)
         rows = np.zeros((tab.shape[0], 12), dtype=np.float32)
         rows[:, 0:3], rows[:, 3] = tab[:, 0:3], tab[:, 9]
@@ -238,7 +258,10 @@ class SwarmCore:
         t.mode, t.num_wp, t.advance_wp = 1, int(tab.shape[0]), 1 if advance else 0
         t.table = d.data_ptr()
         t.offset = off.data_ptr() if off is not None else None
-        t._keep = (d, off)
+        if wp is not None:
+            wp = wp.to(self.device, torch.int32).reshape(self.N).contiguous()
+            t.wp = wp.data_ptr()
+        t._keep = (d, off, wp)
         return t
 
     # ------------------------------------------------------------------ stepping
@@ -314,6 +337,14 @@ class SwarmCore:
         L.check(L.lib().ds_rollout_host(self._h, C.c_void_p(host_pos_yaw.data_ptr()), T, self._p(host_done), self._stream()),
                 self._h)
 
+    def rollout_host_table(self, targets: L.ds_targets, host_wp: torch.Tensor, host_done: Optional[torch.Tensor] = None):
+        """``targets``: a ``targets_table`` (device-resident table + optional per-vehicle offsets); ``host_wp`` [T, N] pinned
+        int32 = the waypoint index of every vehicle for each of T control steps (``ds_rollout_host_table``); synchronises."""
+        T = int(host_wp.shape[0])
+        assert host_wp.dtype == torch.int32 and host_wp.is_contiguous() and host_wp.numel() == T * self.N
+        L.check(L.lib().ds_rollout_host_table(self._h, C.byref(targets), C.c_void_p(host_wp.data_ptr()), T, self._p(host_done),
+                                              self._stream()), self._h)
+
     # ------------------------------------------------------------------ state access
     def views(self) -> dict:
         """Zero-copy torch views of the resident state (valid until ``close``)."""
@@ -333,7 +364,7 @@ class SwarmCore:
             **ext,
             "pos": pos_t[:, :3], "last_thrust": pos_t[:, 3], "quat": quat, "vel": vel_r[:, :3], "rpm_sum": vel_r[:, 3],
             "omega_body": om_w[:, :3], "wp_counter": om_w.view(torch.int32)[:, 3], "last_vel": lv_d[:, :3],
-            "done_bits": lv_d.view(torch.int32)[:, 3], "last_rates": lr_e[:, :3], "pos_err": lr_e[:, 3],
+            "done_bits": lv_d.view(torch.int32)[:, 3] & 0x7FFFFFFF, "last_rates": lr_e[:, :3], "pos_err": lr_e[:, 3],
             "cmd0123": c0, "cmd45": c1, "step_counter": int(v.step_counter),
         }
 

@@ -65,7 +65,26 @@ struct ds_handle {
   uint8_t slot_type[DS_MAX_DRONES_PER_ENV];
   std::vector<DsTypeDev> types_host;  // host copy of the device type table (homogeneous swarms pass theirs by value)
   int homo_type = -1;                 // the one type every slot flies, -1: mixed
+  int32_t* d_env_t0 = nullptr;        // [n_envs] step counter at each env's last masked reset (ds_reset_envs), lazily allocated
+  int32_t* d_roll_wp[2] = {nullptr, nullptr};  // ds_rollout_host_table: double-buffered waypoint indices
 };
+
+// Every entry point runs on the handle's device and puts the caller's current device back on exit: a process that
+// drives several GPUs (or PyTorch's own current-device bookkeeping) must not see it change behind its back.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(h)                        \
+  DeviceGuard guard_((h)->cfg.device);      \
+  CK(guard_.err)
 
 #define CK(call)                                  \
   do {                                            \
@@ -95,7 +114,7 @@ static void free_all(ds_handle* h) {
                   h->d_types, h->d_wls, h->d_slot_type, h->d_init_cmd, h->d_init_thrust, h->d_stats, h->d_stage,
                   h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
                   h->d_roll_done[1], h->d_log_ids, h->d_log_states, h->s_r0, h->s_r1, h->s_af, h->d_wls_count, h->d_wls_index, h->d_wls_nu,
-                  h->d_cmd_scratch, h->d_tile_counter};
+                  h->d_cmd_scratch, h->d_tile_counter, h->d_env_t0, h->d_roll_wp[0], h->d_roll_wp[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int b = 0; b < 2; ++b) {
@@ -126,7 +145,8 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
     delete h;
     return DS_ERR_CUDA;  // no CUDA device: there is deliberately no CPU path
   }
-  if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return DS_ERR_CUDA; }
+  DeviceGuard guard(cfg->device);
+  if (guard.err != cudaSuccess) { delete h; return DS_ERR_CUDA; }
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   const int D = cfg->drones_per_env;
   h->n = cfg->n_envs * D;
@@ -163,7 +183,7 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
 
 extern "C" void ds_destroy(ds_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   free_all(h);
   delete h;
 }
@@ -187,7 +207,7 @@ static bool inv3(const double* m, double* o) {
 
 extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n_types, const uint8_t* slot_type) {
   if (!h || !types || !slot_type || n_types <= 0 || n_types > DS_MAX_TYPES) return DS_ERR_INVALID;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   std::vector<DsTypeDev> dev(DS_MAX_TYPES_DEV);
   std::vector<DsWlsDev> wls(DS_MAX_TYPES_DEV);
   std::vector<float> icmd(DS_MAX_TYPES_DEV, 0.f), ithr(DS_MAX_TYPES_DEV, 0.f);
@@ -342,7 +362,7 @@ extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, cons
                         const int32_t* wp0, void* stream) {
   if (!h || !pos0) return DS_ERR_INVALID;
   if (!h->types_set) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)h->n;
   // staging layout: pos0 | rpy0 | vel0 | action0 | wp0
@@ -366,6 +386,7 @@ extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, cons
   a.action0 = action0 ? d_act : nullptr; a.wp0 = wp0 ? d_wp : nullptr;
   a.slot_type = h->d_slot_type; a.types = h->d_types; a.init_cmd = h->d_init_cmd; a.init_thrust = h->d_init_thrust;
   a.n = h->n; a.n_pad = h->n_pad; a.D = h->cfg.drones_per_env;
+  a.mask = nullptr; a.env_t0 = nullptr; a.step_now = 0;
   ds_reset_kernel<<<grid_for(h, (h->n_pad + 255) / 256, 8), 256, 0, st>>>(a);
   h->launches++;
   if (h->ext) {
@@ -373,6 +394,7 @@ extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, cons
     h->launches++;
   }
   CK(cudaGetLastError());
+  if (h->d_env_t0) CK(cudaMemsetAsync(h->d_env_t0, 0, sizeof(int32_t) * (size_t)h->cfg.n_envs, st));
   CK(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * DS_NUM_STATS, st));
   {
     double big = 1.0e300;
@@ -385,6 +407,35 @@ extern "C" int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, cons
   h->first_action_pending = (action0 != nullptr);
   h->act_valid = (action0 == nullptr);  // obs tail after reset = last_clipped_action = zeros (BaseAviary.py:659-662)
   h->is_reset = true;
+  return DS_OK;
+}
+
+extern "C" int ds_reset_envs(ds_handle* h, const uint8_t* mask_env, const float* pos0, const float* rpy0, const float* vel0,
+                             const float* action0, const int32_t* wp0, void* stream) {
+  if (!h || !mask_env || !pos0) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;  // a full ds_reset comes first (it sizes the staging)
+  ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->d_env_t0) {
+    CK(cudaMalloc((void**)&h->d_env_t0, sizeof(int32_t) * (size_t)h->cfg.n_envs));
+    CK(cudaMemsetAsync(h->d_env_t0, 0, sizeof(int32_t) * (size_t)h->cfg.n_envs, st));
+  }
+  DsResetArgs a;
+  a.s_pos = h->s_pos; a.s_quat = h->s_quat; a.s_vel = h->s_vel; a.s_om = h->s_om; a.s_lv = h->s_lv; a.s_lr = h->s_lr;
+  a.s_c0 = h->s_c0; a.s_a0 = h->s_a0; a.s_c1 = h->s_c1; a.s_a1 = h->s_a1;
+  a.pos0 = pos0; a.rpy0 = rpy0; a.vel0 = vel0; a.action0 = action0; a.wp0 = wp0;
+  a.slot_type = h->d_slot_type; a.types = h->d_types; a.init_cmd = h->d_init_cmd; a.init_thrust = h->d_init_thrust;
+  a.n = h->n; a.n_pad = h->n_pad; a.D = h->cfg.drones_per_env;
+  a.mask = mask_env; a.env_t0 = h->d_env_t0; a.step_now = (int)h->step_counter;
+  ds_reset_kernel<<<grid_for(h, (h->n_pad + 255) / 256, 8), 256, 0, st>>>(a);
+  h->launches++;
+  if (h->ext) {
+    ds_reset_ext_kernel<<<grid_for(h, (h->n_pad + 255) / 256, 8), 256, 0, st>>>(a, h->s_r0, h->s_r1, h->s_af);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  // the obs tail of a reset env is its (zero or initial) action: the action array must stay the obs source only if it
+  // already was; after fused steps the tail is the controller command, which the reset kernel has re-initialised too
   return DS_OK;
 }
 
@@ -418,6 +469,9 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.goal_en = h->cfg.done_goal_enable; a.floor_en = h->cfg.done_floor_enable;
   a.goal_x = h->cfg.goal[0]; a.goal_y = h->cfg.goal[1]; a.goal_z = h->cfg.goal[2]; a.goal_r2 = h->cfg.goal_radius * h->cfg.goal_radius;
   a.z_min = h->cfg.z_min;
+  a.env_t0 = h->d_env_t0;
+  a.max_steps = h->cfg.max_steps;
+  a.step_end = (int)(h->step_counter + h->cfg.substeps);
 }
 
 static int set_targets(DsArgs& a, const ds_targets* t) {
@@ -434,6 +488,8 @@ static int set_targets(DsArgs& a, const ds_targets* t) {
     if (!t->table || t->num_wp <= 0) return DS_ERR_INVALID;
     a.t_table = (const float4*)t->table; a.t_off = (const float4*)t->offset;
     a.num_wp = t->num_wp; a.advance_wp = t->advance_wp;
+    if (((uintptr_t)t->wp & 3u) != 0) return DS_ERR_INVALID;
+    a.t_wp = t->wp;
   } else if (t->mode == 2) {
     if (!t->vel) return DS_ERR_INVALID;
     a.t_vel = (const float4*)t->vel;
@@ -468,12 +524,13 @@ static void set_filter(const ds_handle* h, DsArgs& a) {  // b = 1 - exp(-2 pi f_
 
 static void time_flags(const ds_handle* h, DsArgs& a) {
   a.time_hit = (h->cfg.max_steps > 0 && h->step_counter + h->cfg.substeps >= h->cfg.max_steps) ? 1 : 0;
+  a.step_end = (int)(h->step_counter + h->cfg.substeps);
 }
 
 extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_steps, int32_t order, void* stream) {
   if (!h || n_control_steps < 0 || (order != 0 && order != 1)) return DS_ERR_INVALID;
   if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   DsArgs a;
   base_args(h, a);
   int rc = set_targets(a, tgt);
@@ -484,6 +541,15 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   a.inv_ctrl_dt = h->cfg.sim_freq / (float)h->cfg.substeps;
   set_filter(h, a);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // A captured launch freezes its host-side arguments: the substep index the noise stream is keyed by, the time-limit
+    // flag and the log column would repeat on every replay.  Refuse to capture such a step instead of replaying it wrong.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone &&
+        (h->cfg.noise_force_sigma > 0.f || h->cfg.noise_torque_sigma > 0.f || h->cfg.max_steps > 0 || h->log_n > 0 ||
+         h->first_action_pending))
+      return DS_ERR_UNSUPPORTED;
+  }
   if (order == DS_ORDER_CONTROL_THEN_PHYSICS && h->any_6dof) {
     // The fused kernel defers the rare FP64 WLS iterations to a follow-up kernel, which is too late when the physics of
     // the SAME launch needs the command: run the control kernel (in-line slow path), then the physics with its output.
@@ -540,7 +606,7 @@ extern "C" int ds_set_env_outputs(ds_handle* h, uint8_t* done_env, float* reward
 extern "C" int ds_physics_step(ds_handle* h, const float* action, void* stream) {
   if (!h || !action) return DS_ERR_INVALID;
   if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   DsArgs a;
   base_args(h, a);
   a.ext_action = action;
@@ -561,7 +627,7 @@ static int control_common(ds_handle* h, const float* state, const ds_targets* tg
                           float control_timestep, float* cmd_out, float* pos_e_out, float* yaw_err_out, void* stream) {
   if (!h || !(control_timestep > 0.f)) return DS_ERR_INVALID;
   if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   DsArgs a;
   base_args(h, a);
   if (!rate_thrust) {
@@ -636,7 +702,7 @@ static int log_sample(ds_handle* h, cudaStream_t st) {
 
 extern "C" int ds_log_attach(ds_handle* h, const int32_t* vehicles, int32_t n_vehicles, int32_t capacity) {
   if (!h || n_vehicles < 0 || capacity < 0 || (n_vehicles > 0 && (!vehicles || capacity == 0))) return DS_ERR_INVALID;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   for (int i = 0; i < n_vehicles; ++i)
     if (vehicles[i] < 0 || vehicles[i] >= h->n) return DS_ERR_INVALID;
   if (h->d_log_ids) cudaFree(h->d_log_ids);
@@ -654,7 +720,7 @@ extern "C" int ds_log_attach(ds_handle* h, const int32_t* vehicles, int32_t n_ve
 
 extern "C" int ds_log_read(ds_handle* h, float* host_states, double* host_timestamps, int32_t* count_out, void* stream) {
   if (!h || !count_out) return DS_ERR_INVALID;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   *count_out = h->log_count;
   if (host_states && h->log_n)
     CK(cudaMemcpyAsync(host_states, h->d_log_states, sizeof(float) * (size_t)h->log_n * DS_OBS_STRIDE * h->log_cap,
@@ -669,7 +735,7 @@ extern "C" int ds_get_obs(ds_handle* h, float* obs, uint32_t* neighbors, uint8_t
                           void* stream) {
   if (!h) return DS_ERR_INVALID;
   if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   DsObsArgs a;
   obs_args(h, a);
   a.obs = obs; a.neighbors = neighbors; a.done_env = done_env; a.reward_env = reward_env;
@@ -693,14 +759,14 @@ extern "C" int ds_views(ds_handle* h, ds_state_views* out) {
 
 extern "C" int ds_stats(ds_handle* h, double* host_out, int32_t n, void* stream) {
   if (!h || !host_out || n <= 0 || n > DS_NUM_STATS) return DS_ERR_INVALID;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   CK(cudaMemcpyAsync(host_out, h->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
   return DS_OK;
 }
 extern "C" int ds_stats_reset(ds_handle* h, void* stream) {
   if (!h) return DS_ERR_INVALID;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   CK(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * DS_NUM_STATS, (cudaStream_t)stream));
   double big = 1.0e300;
   CK(cudaMemcpyAsync(h->d_stats + 6, &big, sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -712,7 +778,7 @@ extern "C" int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host
                             void* stream) {
   if (!h || !host_pos_yaw) return DS_ERR_INVALID;
   if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)h->n;
   if (!h->d_host_tgt) CK(cudaMalloc((void**)&h->d_host_tgt, (size_t)h->n_pad * 16));
@@ -735,35 +801,56 @@ extern "C" int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host
   return DS_OK;
 }
 
-extern "C" int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t n_steps, uint8_t* host_done_env,
-                               void* stream) {
-  if (!h || !host_pos_yaw || n_steps <= 0) return DS_ERR_INVALID;
-  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
-  CK(cudaSetDevice(h->cfg.device));
+// One host -> device copy, issued as 8 MiB pieces: with one process per GPU all ranks pull from the same host memory and
+// PCIe root, and pieces let the copies of different ranks interleave instead of queueing behind a whole 64 MiB transfer.
+static cudaError_t h2d_chunked(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const size_t piece = (size_t)8 << 20;
+  for (size_t off = 0; off < bytes; off += piece) {
+    const size_t len = bytes - off < piece ? bytes - off : piece;
+    cudaError_t e = cudaMemcpyAsync((char*)dst + off, (const char*)src + off, len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// The pipelined host rollout behind ds_rollout_host (per-vehicle set-points, 16 B per vehicle and step) and
+// ds_rollout_host_table (per-vehicle waypoint indices into a device-resident table, 4 B).
+static int rollout_common(ds_handle* h, const ds_targets* table_tgt, const void* host_src, size_t bytes_per_step,
+                          int32_t n_steps, uint8_t* host_done_env, void* stream) {
+  ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t n = (size_t)h->n, E = (size_t)h->cfg.n_envs;
+  const size_t E = (size_t)h->cfg.n_envs;
   if (!h->st_h2d) {
     CK(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
-      CK(cudaMalloc((void**)&h->d_roll_tgt[b], (size_t)h->n_pad * 16));
       CK(cudaMalloc((void**)&h->d_roll_done[b], E));
       CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_computed[b], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_drained[b], cudaEventDisableTiming));
     }
   }
+  for (int b = 0; b < 2; ++b) {
+    if (!table_tgt && !h->d_roll_tgt[b]) CK(cudaMalloc((void**)&h->d_roll_tgt[b], (size_t)h->n_pad * 16));
+    if (table_tgt && !h->d_roll_wp[b]) CK(cudaMalloc((void**)&h->d_roll_wp[b], (size_t)h->n_pad * sizeof(int32_t)));
+  }
   for (int i = 0; i < n_steps; ++i) {
     const int b = i & 1;
-    // targets of step i -> device buffer b (free once step i-2 has consumed it)
+    void* dst = table_tgt ? (void*)h->d_roll_wp[b] : (void*)h->d_roll_tgt[b];
+    // inputs of step i -> device buffer b (free once step i-2 has consumed it)
     if (i >= 2) CK(cudaStreamWaitEvent(h->st_h2d, h->ev_computed[b], 0));
-    CK(cudaMemcpyAsync(h->d_roll_tgt[b], host_pos_yaw + (size_t)i * n * 4, n * 16, cudaMemcpyHostToDevice, h->st_h2d));
+    CK(h2d_chunked(dst, (const char*)host_src + (size_t)i * bytes_per_step, bytes_per_step, h->st_h2d));
     CK(cudaEventRecord(h->ev_copied[b], h->st_h2d));
     CK(cudaStreamWaitEvent(st, h->ev_copied[b], 0));
     ds_targets t;
-    memset(&t, 0, sizeof(t));
-    t.mode = 0;
-    t.pos_yaw = (const float*)h->d_roll_tgt[b];
+    if (table_tgt) {
+      t = *table_tgt;
+      t.wp = h->d_roll_wp[b];
+    } else {
+      memset(&t, 0, sizeof(t));
+      t.mode = 0;
+      t.pos_yaw = (const float*)h->d_roll_tgt[b];
+    }
     // the per-env done flags of step i are reduced inside the step kernel (warp shuffles) straight into buffer b
     uint8_t* const saved_done = h->env_done_out;
     float* const saved_reward = h->env_reward_out;
@@ -789,12 +876,26 @@ extern "C" int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t 
   return DS_OK;
 }
 
+extern "C" int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t n_steps, uint8_t* host_done_env,
+                               void* stream) {
+  if (!h || !host_pos_yaw || n_steps <= 0) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  return rollout_common(h, nullptr, host_pos_yaw, (size_t)h->n * 16, n_steps, host_done_env, stream);
+}
+
+extern "C" int ds_rollout_host_table(ds_handle* h, const ds_targets* tgt, const int32_t* host_wp, int32_t n_steps,
+                                     uint8_t* host_done_env, void* stream) {
+  if (!h || !tgt || !host_wp || n_steps <= 0 || tgt->mode != 1 || !tgt->table || tgt->num_wp <= 0) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  return rollout_common(h, tgt, host_wp, (size_t)h->n * sizeof(int32_t), n_steps, host_done_env, stream);
+}
+
 extern "C" int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out,
                             int32_t* iter_out, int32_t* w_out, int32_t n, int32_t force_slow, void* stream) {
   if (!h || !v || !cmd || !du_out || !iter_out || n <= 0) return DS_ERR_INVALID;
   if (!h->types_set) return DS_ERR_STATE;
   if (type_id < 0 || type_id >= h->n_types) return DS_ERR_INVALID;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   ds_wls_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_types, h->d_wls, type_id, v, cmd, du_out, iter_out, w_out, n,
                                                                force_slow);
   h->launches++;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) ds_obs_kernel(const DsObsArgs a) {
       // env done: slot 0 reached the goal (the example tests drone "0"), any slot under the floor / out of time
       uint32_t any = 0;
       for (int j = 0; j < a.D; ++j) {
-        uint32_t b = __float_as_uint(a.s_lv[env0 + j].w);
+        uint32_t b = __float_as_uint(a.s_lv[env0 + j].w) & ~DS_PENDING_ACTION;
         any |= (j == 0) ? b : (b & 6u);
       }
       if (a.done_env) a.done_env[v / a.D] = any ? 1 : 0;
@@ -179,11 +179,19 @@ struct DsResetArgs {
   const float* init_cmd;     // [n_types]
   const float* init_thrust;  // [n_types]
   int n, n_pad, D;
+  // masked reset (ds_reset_envs): only envs with mask[env] != 0 are touched; their time origin becomes step_now
+  const uint8_t* mask;
+  int32_t* env_t0;
+  int step_now;
 };
 
 __global__ void __launch_bounds__(256) ds_reset_kernel(const DsResetArgs a) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n_pad; v += gridDim.x * blockDim.x) {
     const bool real = v < a.n;
+    if (a.mask) {
+      if (!real || !a.mask[v / a.D]) continue;
+      if (v % a.D == 0 && a.env_t0) a.env_t0[v / a.D] = a.step_now;
+    }
     const int type_id = real ? a.slot_type[v % a.D] : 0;
     float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
     double r = 0.0, p = 0.0, y = 0.0;
@@ -204,7 +212,8 @@ __global__ void __launch_bounds__(256) ds_reset_kernel(const DsResetArgs a) {
     a.s_quat[v] = make_float4((float)(qx * n), (float)(qy * n), (float)(qz * n), (float)(qw * n));
     a.s_vel[v] = make_float4(vx, vy, vz, real ? a.types[type_id].rpm0_sum : 0.f);
     a.s_om[v] = make_float4(0.f, 0.f, 0.f, __int_as_float((real && a.wp0) ? a.wp0[v] : 0));
-    a.s_lv[v] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    // a masked reset cannot use the launch-wide "first action pending" flag: the vehicle carries it in bit 31
+    a.s_lv[v] = make_float4(0.f, 0.f, 0.f, __uint_as_float((a.mask && a.action0) ? DS_PENDING_ACTION : 0u));
     a.s_lr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     a.s_c0[v] = make_float4(nu > 0 ? ic : 0.f, nu > 1 ? ic : 0.f, nu > 2 ? ic : 0.f, nu > 3 ? ic : 0.f);
     a.s_c1[v] = make_float2(nu > 4 ? ic : 0.f, nu > 5 ? ic : 0.f);
@@ -268,6 +277,7 @@ __global__ void __launch_bounds__(128) ds_wls_fixup_kernel(const DsArgs a) {
 __global__ void __launch_bounds__(256) ds_reset_ext_kernel(const DsResetArgs a, float4* s_r0, float2* s_r1, float4* s_af) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n_pad; v += gridDim.x * blockDim.x) {
     float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a.mask && (v >= a.n || !a.mask[v / a.D])) continue;
     if (v < a.n) {
       const DsTypeDev& tp = a.types[a.slot_type[v % a.D]];
       for (int i = 0; i < tp.n_u; ++i) r[i] = tp.rotor[i].cnst;  // last_clipped_action = 0 after reset (BaseAviary.py:659-662)

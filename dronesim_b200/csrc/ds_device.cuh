@@ -142,8 +142,11 @@ struct DsArgs {
   const float4* t_acc;
   const float4* t_table;
   const float4* t_off;
+  const int32_t* t_wp;   // table mode: the caller's waypoint index per vehicle (nullptr: the resident counter)
   // done predicate
   int goal_en, floor_en, time_hit;
+  const int32_t* env_t0; // per-env step counter at its last masked reset (nullptr: no masked reset yet, time_hit applies)
+  int step_end, max_steps;  // step counter after this launch; per-env time limit: step_end - env_t0[env] >= max_steps
   float goal_x, goal_y, goal_z, goal_r2;   // goal_r2 = fl(r * r): the predicate compares squared distances
   float z_min;
   // per-env outputs of the fused step (optional, DEVICE): reduced with warp shuffles inside the step kernel when every env
@@ -163,6 +166,7 @@ struct DsArgs {
 // ---------------------------------------------------------------------------------------------
 // small math
 // ---------------------------------------------------------------------------------------------
+#define DS_PENDING_ACTION 0x80000000u  // done-bits word, bit 31: the action array holds this vehicle's first action (masked reset)
 #define DS_PI_F 3.14159265358979323846f
 #define DS_GIMBAL 0.99999f
 

@@ -170,13 +170,16 @@ __device__ __forceinline__ CtrlTarget ds_fetch_target(const DsArgs& a, const DsT
     if (a.t_vel) { float4 q = __ldg(a.t_vel + v); t.vx = q.x; t.vy = q.y; t.vz = q.z; }
     if (a.t_acc) { float4 q = __ldg(a.t_acc + v); t.ax = q.x; t.ay = q.y; t.az = q.z; }
   } else {
-    wp = min(max(wp, 0), a.num_wp - 1);  // a counter left over from a longer table must not read past this one
-    const float4* row = a.t_table + 3 * wp;
+    // the caller's index for this step (fly_INDI.py:230-245), else the resident counter; either is clamped: an index left
+    // over from a longer table must not read past this one
+    int w = a.t_wp ? __ldg(a.t_wp + v) : wp;
+    w = min(max(w, 0), a.num_wp - 1);
+    const float4* row = a.t_table + 3 * w;
     float4 p = __ldg(row), q = __ldg(row + 1), r = __ldg(row + 2);
     t.x = p.x; t.y = p.y; t.z = p.z; t.yaw = p.w;
     t.vx = q.x; t.vy = q.y; t.vz = q.z; t.ax = r.x; t.ay = r.y; t.az = r.z;
     if (a.t_off) { const float4 o = *tg0; t.x += o.x; t.y += o.y; t.z += o.z; }
-    if (a.advance_wp) wp = (wp < a.num_wp - 1) ? wp + 1 : 0;  // fly_INDI.py:242-245
+    if (!a.t_wp) wp = a.advance_wp ? ((w < a.num_wp - 1) ? w + 1 : 0) : w;  // fly_INDI.py:242-245
   }
   return t;
 }
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __g
       } else {
         m.cmd[4] = m.cmd[5] = 0.f;
       }
-      done_bits = __float_as_uint(LV.w);
+      done_bits = __float_as_uint(LV.w) & ~DS_PENDING_ACTION;
       if (EXT) { const float4 AF = a.s_af[vv]; m.afx = AF.x; m.afy = AF.y; m.afz = AF.z; }
       CtrlState cs = {s.px, s.py, s.pz, s.qx, s.qy, s.qz, s.qw, s.vx, s.vy, s.vz, s.wx, s.wy, s.wz};
       const float4* tg0 = sg + SG_TG * T + ld;
@@ -309,7 +312,8 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __g
       const float* ea = a.ext_action + (size_t)vv * 6;
 #pragma unroll
       for (int i = 0; i < NU; ++i) act[i] = ds_clampf(ea[i], tp.rotor[i].pmin, tp.rotor[i].pmax);
-    } else if (a.use_act) {  // first step after reset: the caller's initial action (fly_INDI.py:214)
+    } else if (a.use_act || (__float_as_uint(sg[SG_LV * T + ld].w) & DS_PENDING_ACTION)) {
+      // first step after a reset (of the whole batch, or of this vehicle's env): the caller's initial action (fly_INDI.py:214)
       const float4 A0 = a.s_a0[vv];
       act[0] = A0.x; act[1] = A0.y; act[2] = A0.z; act[3] = A0.w;
       if (NU6) { const float2 A1 = a.s_a1[vv]; act[4] = A1.x; act[5] = A1.y; }
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __g
     }
     ds_physics<INTEG, DW, NU6, WARPSYNC, FX, EXT, RC>(a, tp, env_row0, my_row, sh_pos, act, s, prev_rpm_sum, rpm, a.veh0 + (uint32_t)vv);
     if (MODE == 0) control();
-    if (MODE == 1) done_bits = __float_as_uint(sg[SG_LV * T + ld].w);
+    if (MODE == 1) done_bits = __float_as_uint(sg[SG_LV * T + ld].w) & ~DS_PENDING_ACTION;
 
     // ---- done predicate on the fresh state (fly_INDI_TrajectoryTrack.py:249-250)
     // |pos - goal|^2 < r^2 in a fixed order of correctly rounded operations (no contraction, no square root), so the bit
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __g
       if (d2 < a.goal_r2) done_bits |= 1u;
     }
     if (a.floor_en && s.pz < a.z_min) done_bits |= 2u;
-    if (a.time_hit) done_bits |= 4u;
+    if (a.env_t0 ? (a.max_steps > 0 && a.step_end - __ldg(a.env_t0 + vv / a.D) >= a.max_steps) : (a.time_hit != 0)) done_bits |= 4u;
 
     // ---- per-env done / reward (CtrlAviary._computeDone / _computeReward, CtrlAviary.py:267-293, batched): a butterfly of
     // warp shuffles over the D lanes of the env, the env's slot 0 writes.  Same rule as ds_obs_kernel: the goal bit counts

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 1
+#define DS_ABI_VERSION 2
 #define DS_MAX_ROTORS 6
 #define DS_MAX_TYPES 8
 #define DS_MAX_DRONES_PER_ENV 32
@@ -160,6 +160,10 @@ typedef struct ds_targets {
   const float* acc;      /* mode 0: DEVICE [N][4] (xyz used) or NULL = zeros */
   const float* table;    /* mode 1: DEVICE [num_wp][12] = pos xyz,yaw | vel xyz,0 | acc xyz,0 */
   const float* offset;   /* mode 1: DEVICE [N][4] additive position offset or NULL */
+  const int32_t* wp;     /* mode 1: DEVICE [N] waypoint index of every vehicle for THIS control step, supplied by the
+                            caller the way the reference scripts index TARGET_POS[wp_counters[j]] (fly_INDI.py:230-245),
+                            or NULL = the resident per-vehicle counter (which advance_wp then advances).  Indices are
+                            clamped to [0, num_wp). */
 } ds_targets;
 
 /* Borrowed device pointers of the resident state (structure of float4 arrays, each [n_pad]). */
@@ -193,6 +197,15 @@ int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n_types, con
  * or NULL = zeros; wp0 [N] int32 or NULL = zeros. */
 int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, const float* vel0, const float* action0,
              const int32_t* wp0, void* stream);
+
+/* BaseAviary.reset (BaseAviary.py:406-424) for SOME environments of the batch, on the device and without a host
+ * synchronisation: every env e with mask_env[e] != 0 gets exactly the state ds_reset would give it (kinematics,
+ * controller memory, done bits cleared, waypoint counter, and - when action0 is given - action0 as the first applied
+ * action, fly_INDI.py:214); the other envs are not touched.  All pointers DEVICE: mask_env [n_envs] uint8; pos0 [N][3];
+ * rpy0 / vel0 [N][3], action0 [N][DS_MAX_ROTORS], wp0 [N] or NULL; rows of unmasked envs are not read.  The time limit
+ * (max_steps) of a reset env counts from this call.  Stream-ordered. */
+int ds_reset_envs(ds_handle* h, const uint8_t* mask_env, const float* pos0, const float* rpy0, const float* vel0,
+                  const float* action0, const int32_t* wp0, void* stream);
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* n_control_steps x { K physics substeps with the held command ; one INDI evaluation } fused in
@@ -262,6 +275,12 @@ int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host_obs, uint8
  * fly_INDI_TrajectoryTrack.py:133-160).  Every step still pays its own H2D / D2H; they just overlap.
  * Synchronises before returning. */
 int ds_rollout_host(ds_handle* h, const float* host_pos_yaw, int32_t n_steps, uint8_t* host_done_env, void* stream);
+/* The same pipeline fed the way the reference scripts feed their controllers: a waypoint table resident on the device
+ * (tgt: mode 1, DEVICE table and optional DEVICE per-vehicle offsets) and, per control step, ONE index per vehicle
+ * (host_wp HOST [n_steps][N] int32, pinned) - fly_INDI.py:230-245 passes TARGET_POS[wp_counters[j]].  4 bytes per vehicle
+ * and step cross the bus instead of 16. */
+int ds_rollout_host_table(ds_handle* h, const ds_targets* tgt, const int32_t* host_wp, int32_t n_steps,
+                          uint8_t* host_done_env, void* stream);
 
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* The 6-DOF allocation alone: wls_alloc(v, MIN-cmd, MAX-cmd, G1/0.05, None, None, Wv, 1, None)

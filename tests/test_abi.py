@@ -63,7 +63,7 @@ def test_struct_layouts_match_header(lib):
 
 
 def test_misc_entry_points(lib):
-    assert lib.ds_abi_version() == 1
+    assert lib.ds_abi_version() == 2
     assert lib.ds_strerror(0) == b"ok"
     assert b"no CPU fallback" in lib.ds_strerror(2)
     assert lib.ds_launch_count(None) == 0

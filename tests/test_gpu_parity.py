@@ -306,7 +306,7 @@ def test_wls_vs_reference_fixture():
     _need_gpu()
     from dronesim_b200.core import SwarmCore
 
-    g = np.load(os.path.join(GOLD, "wls_cases.npz"))
+    g = dict(np.load(os.path.join(GOLD, "wls_cases.npz")))
     core = SwarmCore(["hexa_6DOF"], 1)
     v = torch.tensor(g["rnd_v"], dtype=torch.float32)
     cmd = torch.tensor(g["rnd_cmd"], dtype=torch.float32)
@@ -1022,3 +1022,186 @@ def test_cuda_graph_replay_of_fused_steps():
         np.testing.assert_array_equal(vg[k].cpu().numpy(), ve[k].cpu().numpy(), err_msg=k)
     eager.close()
     graph_core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE configs[0]: examples/fly_INDI.py for its full 10 s on the reference's own explicit-dynamics (DYN) formulas
+# (BaseAviary.py:1767-1828, DS_INTEG_RPY) - 480 control steps x 5 substeps at 240 Hz
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("integrator", ["rpy", "quat"])
+def test_cfg1_hover_robobee_10s(integrator):
+    _need_gpu()
+    core, orc = make_pair(["robobee"], 1, integrator, K=5)
+    pos0 = np.array([[0.0, 1.0, 0.5]])
+    act0 = np.zeros((1, 6))
+    act0[:, :4] = 0.4
+    num_wp = 48 * 15
+    tab = _table(num_wp, np.array([0.0, 0.0, 0.5]), lambda i: 0.4 + i / 200.0)
+    core.reset(pos0, action0=act0)
+    orc.reset(pos0)
+    tgt = core.targets_table(tab)
+    wp = np.zeros(1, dtype=np.int64)
+    act = act0.reshape(1, 1, 6).copy()
+    worst = 0.0
+    for step in range(480):
+        core.step(tgt, 1)
+        orc.physics_step(act)
+        act = orc.control_step(tab[wp, 0:3].reshape(1, 1, 3), tyaw=tab[wp, 9].reshape(1, 1))
+        wp = np.where(wp < num_wp - 1, wp + 1, 0)
+        if step % 48 == 47:  # once per simulated second
+            worst = max(worst, float(np.abs(core_state(core)["pos"] - orc.pos.reshape(1, 3)).max()))
+    _compare_state(core, orc, pos_tol=3e-4, att_tol=3e-4, what="cfg1 10 s/" + integrator)
+    assert worst <= 3e-4
+    assert core_state(core)["step_counter"] == orc.step_counter == 2400
+    assert int(core.views()["wp_counter"][0]) == int(wp[0]) == 480
+    # the hover is reached and held: within 5 mm of the set-point after 10 s
+    assert np.abs(core_state(core)["pos"][0] - np.array([0.0, 0.0, 0.5])).max() < 5e-3
+    core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# what bench.py runs: the hetero16 swarm of dronesim_b200.workloads, 1 s closed loop - against the per-vehicle oracle
+# (3 envs) and the vectorised oracle (64 envs)
+# ------------------------------------------------------------------------------------------
+def test_bench_workload_hetero16_vs_oracles():
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.vehicles import load_vehicle
+    from dronesim_b200.workloads import hetero16
+    from oracle.batch import BatchOracle
+
+    E = 64
+    models, K, flags, pos0, act0, tgt = hetero16(E, seed=0)
+    vts = [load_vehicle(m) for m in models]
+    core = SwarmCore(vts, E, integrator="quat", aggregate_phy_steps=K, stats=True, **flags)
+    core.reset(pos0, action0=act0)
+    targets = core.targets_per_vehicle(tgt)
+    bo = BatchOracle(vts, E, gnd=flags["ground"], drag=flags["drag"], dw=flags["downwash"], aggregate_phy_steps=K)
+    bo.reset(pos0)
+    E3 = 3
+    orc = OracleSwarm(vts, E3, integrator="quat", composite=True, gnd=flags["ground"], drag=flags["drag"], dw=flags["downwash"],
+                      aggregate_phy_steps=K)
+    orc.reset(pos0[:E3])
+    tpos = tgt[:, :3].reshape(E, 16, 3)
+    act_b, act_o = act0.copy(), act0[:E3].copy()
+    for step in range(30):  # 30 control steps x 8 substeps = 1 s
+        core.step(targets, 1)
+        bo.physics_step(act_b)
+        act_b = bo.control_step(tpos)
+        orc.physics_step(act_o)
+        act_o = orc.control_step(tpos[:E3])
+    _compare_state(core, bo, what="hetero16 vs vectorised oracle")
+    st = core_state(core)
+    n3 = E3 * 16
+    assert np.abs(st["pos"][:n3] - orc.pos.reshape(n3, 3)).max() <= POS_TOL
+    assert angle_between(st["quat"][:n3], orc.quat.reshape(n3, 4)).max() <= ATT_TOL
+    assert core.stats()["non_finite"] == 0
+    core.close()
+
+
+# ------------------------------------------------------------------------------------------
+# masked device-side reset (BaseAviary.reset per environment): untouched envs bit-identical, reset envs == a fresh handle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("models,flags", [(["robobee"], {}), (["tello", "hexa_6DOF", "robobee", "hexa_6DOF"], dict(ground=True, drag=True, downwash=True))])
+def test_reset_envs_masked(models, flags):
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    D, E, K = len(models), 37, 4
+    rng = np.random.default_rng(9)
+    pos0 = np.zeros((E, D, 3))
+    for s in range(D):
+        pos0[:, s] = [1.2 * s, 0.0, 1.0 + 0.4 * s]
+    pos0 += rng.uniform(-0.05, 0.05, pos0.shape)
+    act0 = np.full((E, D, 6), 0.42)
+    tgt_np = np.concatenate([pos0.reshape(-1, 3) + 0.1, np.zeros((E * D, 1))], axis=1)
+    mask = (rng.uniform(size=E) < 0.4)
+    mask[0], mask[-1] = True, False
+    pos1 = pos0 + rng.uniform(-0.2, 0.2, pos0.shape)   # where the reset envs restart
+    rpy1 = rng.uniform(-0.2, 0.2, (E, D, 3))
+    act1 = np.full((E, D, 6), 0.37)
+    kw = dict(aggregate_phy_steps=K, max_steps=40, z_min=0.0, **flags)
+    a = SwarmCore(models, E, **kw)      # steps 6, masked reset, steps 5
+    b = SwarmCore(models, E, **kw)      # steps 11 without reset: the untouched envs
+    c = SwarmCore(models, E, **kw)      # fresh handle reset to the new poses, steps 5: the reset envs
+    for core_ in (a, b):
+        core_.reset(pos0, action0=act0)
+    c.reset(pos1, rpy0=rpy1, action0=act1)
+    ta, tb, tc = (x.targets_per_vehicle(tgt_np) for x in (a, b, c))
+    a.step(ta, 6)
+    b.step(tb, 6)
+    a.reset_envs(mask, pos1, rpy0=rpy1, action0=act1)
+    va = a.views()
+    assert (va["done_bits"].cpu().numpy() >= 0).all()
+    a.step(ta, 5)
+    b.step(tb, 5)
+    c.step(tc, 5)
+    vm = np.repeat(mask, D)
+    va, vb, vc = a.views(), b.views(), c.views()
+    for k in ("pos", "quat", "vel", "omega_body", "last_vel", "last_rates", "last_thrust", "cmd0123", "cmd45", "wp_counter", "pos_err"):
+        xa, xb, xc = va[k].cpu().numpy(), vb[k].cpu().numpy(), vc[k].cpu().numpy()
+        np.testing.assert_array_equal(xa[~vm], xb[~vm], err_msg="untouched env changed: " + k)
+        np.testing.assert_array_equal(xa[vm], xc[vm], err_msg="reset env differs from a fresh handle: " + k)
+    # time limit per env: the untouched envs have run 11 x 4 = 44 >= 40 substeps, the reset ones 20
+    da = va["done_bits"].cpu().numpy()
+    assert ((da[~vm] & 4) != 0).all() and ((da[vm] & 4) == 0).all()
+    for x in (a, b, c):
+        x.close()
+
+
+# ------------------------------------------------------------------------------------------
+# table targets with the caller's waypoint indices (fly_INDI.py:230-245) == the resident counters; host rollout of
+# indices == device-resident steps; a homogeneous swarm's kernel variant == the mixed-swarm variant, bit for bit
+# ------------------------------------------------------------------------------------------
+def test_external_waypoint_indices_rollout_and_homogeneous_variant():
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    g = np.load(os.path.join(GOLD, "traj_3gates.npz"))
+    tab = g["table"]
+    E, T = 300, 7
+    rng = np.random.default_rng(2)
+    pos0 = np.array([-3.0, 0.0, 2.0]) + rng.uniform(-0.05, 0.05, (E, 3))
+    act0 = np.zeros((E, 6))
+    act0[:, :4] = 0.4
+    wp0 = ((np.arange(E) * 7) % tab.shape[0]).astype(np.int32)
+    cores = [SwarmCore(["robobee"], E, aggregate_phy_steps=2, types_in_smem=(i == 3)) for i in range(4)]
+    for c in cores:
+        c.reset(pos0, action0=act0, wp0=wp0)
+    # 0: resident counters; 1: caller's indices per step; 2: host rollout of indices; 3: resident counters, mixed-swarm kernel
+    wp_seq = np.stack([(wp0 + t) % tab.shape[0] for t in range(T)]).astype(np.int32)
+    cores[0].step(cores[0].targets_table(tab), T)
+    cores[3].step(cores[3].targets_table(tab), T)
+    for t in range(T):
+        cores[1].step(cores[1].targets_table(tab, wp=torch.tensor(wp_seq[t], device="cuda")), 1)
+    h_wp = torch.from_numpy(wp_seq).contiguous().pin_memory()
+    h_done = torch.zeros((T, E), dtype=torch.uint8).pin_memory()
+    cores[2].rollout_host_table(cores[2].targets_table(tab), h_wp, h_done)
+    v = [c.views() for c in cores]
+    for k in ("pos", "quat", "vel", "omega_body", "cmd0123", "last_vel", "last_rates"):
+        for i in (1, 2, 3):
+            np.testing.assert_array_equal(v[i][k].cpu().numpy(), v[0][k].cpu().numpy(), err_msg="%s core %d" % (k, i))
+    np.testing.assert_array_equal(v[0]["wp_counter"].cpu().numpy(), (wp0 + T) % tab.shape[0])
+    np.testing.assert_array_equal(v[1]["wp_counter"].cpu().numpy(), wp0)  # the caller's indices leave the resident counter alone
+    assert not h_done.numpy().any()
+    for c in cores:
+        c.close()
+
+
+def test_cuda_graph_capture_refuses_frozen_host_arguments():
+    """A captured step freezes the time-limit flag (and the noise counter / log column): refused, not replayed wrong."""
+    _need_gpu()
+    from dronesim_b200 import _lib as L
+    from dronesim_b200.core import SwarmCore
+
+    core = SwarmCore(["robobee"], 8, aggregate_phy_steps=2, max_steps=100)
+    core.reset(np.tile([0.0, 0.0, 1.0], (8, 1)))
+    tgt = core.targets_per_vehicle(np.tile([0.0, 0.0, 1.0, 0.0], (8, 1)))
+    core.step(tgt, 1)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with pytest.raises(L.DsError):
+            with torch.cuda.graph(g, stream=s):
+                core.step(tgt, 1)
+    core.close()

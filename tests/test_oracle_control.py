@@ -15,7 +15,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_wls_known_answer_matlab():
-    g = np.load(os.path.join(GOLD, "wls_cases.npz"))
+    g = dict(np.load(os.path.join(GOLD, "wls_cases.npz")))
     du, it = oc.wls_alloc(g["kat_v"], g["kat_umin"], g["kat_umax"], g["kat_B"], None, None, g["kat_Wv"], None, g["kat_up"])
     assert it == int(g["kat_iter"]) == 6  # integer-exact iteration count
     np.testing.assert_allclose(du, g["kat_du"], rtol=0, atol=1e-9)  # == the reference function's output
@@ -23,7 +23,7 @@ def test_wls_known_answer_matlab():
 
 
 def test_wls_random_cases_iterations_and_active_set():
-    g = np.load(os.path.join(GOLD, "wls_cases.npz"))
+    g = dict(np.load(os.path.join(GOLD, "wls_cases.npz")))
     B, Wv = g["rnd_B"], g["rnd_Wv"]
     # the oracle is a pure-Python loop: every 5th of the 10,240 reference cases, plus every non-converging one (whose 100
     # iterations dominate the time: keep 12 of them)
@@ -43,7 +43,7 @@ def test_wls_random_cases_iterations_and_active_set():
 
 def test_wls_first_iteration_matrix_is_the_closed_form():
     """iteration 1 is du = M nu with the per-type constant the CUDA core keeps in shared memory."""
-    g = np.load(os.path.join(GOLD, "wls_cases.npz"))
+    g = dict(np.load(os.path.join(GOLD, "wls_cases.npz")))
     M = load_vehicle("hexa_6DOF").wls_unconstrained()
     one = (g["rnd_iter"] == 1) & g["rnd_ok"]
     assert one.sum() > 100

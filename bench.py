@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 50)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="control steps of the CPU baseline sample; 0 = sized for ~12 s")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary (single-type) workloads")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 1 Mi / 16 Mi / 64 Mi points of the configs[4] sweep")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run check of the timed swarm against the FP64 oracle")
+    ap.add_argument("--parity-envs", type=int, default=128, help="environments of the timed swarm checked against the oracle")
     return ap.parse_args()
 
 
@@ -68,7 +71,9 @@ def workload_config(envs_per_gpu: int, n_gpus: int) -> dict:
     return {
         "workload": "hetero16 swarm (BASELINE configs[3]/[4]): %d envs x 16 drones = %d vehicles per GPU, "
                     "8 quad (robobee/tello) + 8 hexa_6DOF per env, ground effect + drag + downwash, K=8 substeps "
-                    "fused per INDI control step, hover targets, quaternion integrator" % (envs_per_gpu, envs_per_gpu * DRONES),
+                    "fused per INDI control step, hover targets, quaternion integrator; layout 4x4 grid at 1.0 m pitch, "
+                    "z = 2.0 + 0.25 slot (SURVEY 8d sketches 0.5 m pitch: the reference's downwash term is singular for "
+                    "laterally close vehicles crossing altitudes, dronesim_b200/workloads.py)" % (envs_per_gpu, envs_per_gpu * DRONES),
         "vehicles_per_gpu": envs_per_gpu * DRONES,
         "vehicles_total": envs_per_gpu * DRONES * n_gpus,
         "substeps_per_control_step": K_SUBSTEPS,
@@ -166,40 +171,83 @@ def hbm_peak():
 
 
 # --------------------------------------------------------------------------------------------
+def cpu_arms(kinds, cores, budget_s=12.0):
+    """Time the CPU implementations of the same workload on the host cores (oracle/cpu_bench.py), each on a bounded sample
+    sized from a 2-step calibration to about ``budget_s`` seconds.  Returns {kind: result}."""
+    from oracle.cpu_bench import time_oracle
+
+    out = {}
+    for kind in kinds:
+        epw = 64 if kind == "vectorised" else 1
+        try:
+            cal = time_oracle(steps=2, warmup=1, workers=cores, envs_per_worker=epw, kind=kind)
+            n = int(min(600, max(3, round(budget_s / max(cal["seconds"] / 2.0, 1e-3)))))
+            r = time_oracle(steps=n, warmup=1, workers=cores, envs_per_worker=epw, kind=kind)
+            out[kind] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": r["sample"],
+                         "seconds": r["seconds"], "finite": r["finite"]}
+        except Exception as e:  # a CPU arm must never take the GPU numbers down with it
+            out[kind] = {"value": None, "unit": UNIT, "cores": cores, "kind": kind, "error": repr(e)[:200]}
+    return out
+
+
 def run_reference(args):
     """The reference arm: the reference's own algorithm for this path on the host cores.
 
-    The reference's implementation of the path cannot run on the GPU box (or anywhere without
-    PyBullet; its explicit-dynamics code is dead), so this arm times the oracle
-    port: one process per core, each stepping whole hetero16 envs."""
+    The reference's implementation of the path cannot be stepped as shipped (its explicit-dynamics code is dead and the
+    live path needs PyBullet).  Where the reference checkout exists (this container) its own
+    INDIControl / INDIControl_6DOF classes run behind a three-function pybullet shim next to the restated substep
+    (``kind: reference-executed``); on the GPU box, which has no checkout, the oracle port runs (``kind: port``).
+    One process per core, each stepping whole hetero16 envs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle.cpu_bench import time_oracle
+    from oracle.cpu_bench import reference_available, time_oracle
 
     cores = os.cpu_count() or 1
+    kind = "reference-executed" if reference_available() else "port"
     # bounded sample: one env (16 vehicles) per core per step is ~0.2 s of Python, so the driver's --steps/--warmup
     # are honoured exactly up to 1000/100 steps (~4 min); beyond that they are clamped (and the line says so)
     steps = max(1, min(args.steps, 1000))
     warm = max(1, min(args.warmup, 100))
-    r = time_oracle(steps=steps, warmup=warm, workers=cores, envs_per_worker=1)
+    r = time_oracle(steps=steps, warmup=warm, workers=cores, envs_per_worker=1, kind=kind)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.envs, args.gpus),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference" if kind == "reference-executed" else "port",
+                         "detail": kind, "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU port of the reference path (oracle/), requested steps=%d warmup=%d clamped to %d/%d to bound the run; "
-                "the reference's own implementation of this path is not runnable (dead DYN code, PyBullet absent)"
-                % (args.steps, args.warmup, steps, warm),
+        "note": "CPU implementation of the reference path (%s), requested steps=%d warmup=%d clamped to %d/%d to bound the run"
+                % (kind, args.steps, args.warmup, steps, warm),
     }
     _emit(line)
     return 0
 
 
 # --------------------------------------------------------------------------------------------
+def timed_steps(core, targets, steps, barrier, max_over_ranks, torch):
+    """EXACTLY ``steps`` control steps between barriers, one CUDA event per step on the launching stream.
+    -> (total ms: max over ranks, per-step ms list of this rank)"""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(steps):
+        core.step(targets, 1)
+        evs[i + 1].record()
+    barrier()
+    total = max_over_ranks(evs[0].elapsed_time(evs[steps]))
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return total, per
+
+
+def spread(per):
+    s = sorted(per)
+    n = len(s)
+    return {"median_ms": s[n // 2], "p95_ms": s[min(n - 1, int(0.95 * n))], "min_ms": s[0], "max_ms": s[-1]}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -208,6 +256,7 @@ def run_ours(args):
     from dronesim_b200 import _lib as L
     from dronesim_b200.core import SwarmCore
     from dronesim_b200.sharding import allreduce_stats
+    from dronesim_b200.vehicles import load_vehicle
     from dronesim_b200.workloads import hetero16, hetero16_bytes_per_control_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,13 +290,42 @@ def run_ours(args):
     models, K, flags, pos0, act0, tgt = hetero16(E, seed=0, env_offset=rank * E)
     core = SwarmCore(models, E, integrator="quat", aggregate_phy_steps=K, stats=True, device=local_rank,
                      env_offset=rank * E, **flags)
-    core.reset(pos0, action0=act0)
-    del pos0, act0
     tgt32 = np.ascontiguousarray(tgt, dtype=np.float32)
     d_tgt = torch.from_numpy(tgt32).to(dev)
     d_vel = torch.zeros((N, 4), dtype=torch.float32, device=dev)
     d_acc = torch.zeros((N, 4), dtype=torch.float32, device=dev)
     targets = core.targets_per_vehicle(d_tgt, vel=d_vel, acc=d_acc)
+
+    # ---- parity of what is about to be timed: the first envs of this very swarm, 1 s closed loop, against the FP64 oracle
+    parity = None
+    if not args.no_parity:
+        core.reset(pos0, action0=act0)
+        pe, ps = min(args.parity_envs, E), 30  # 30 control steps x 8 substeps = 1 s at 240 Hz
+        core.step(targets, ps)
+        v = core.views()
+        g_pos = v["pos"][: pe * DRONES].cpu().numpy().astype(np.float64)
+        g_quat = v["quat"][: pe * DRONES].cpu().numpy().astype(np.float64)
+        if rank == 0:
+            from oracle.batch import BatchOracle
+
+            bo = BatchOracle([load_vehicle(m) for m in models], pe, gnd=flags["ground"], drag=flags["drag"], dw=flags["downwash"],
+                             aggregate_phy_steps=K)
+            bo.reset(pos0[:pe])
+            act = act0[:pe].copy()
+            tp = tgt[: pe * DRONES, :3].reshape(pe, DRONES, 3)
+            for _ in range(ps):
+                bo.physics_step(act)
+                act = bo.control_step(tp)
+            dq = np.abs(np.sum(g_quat * bo.quat.reshape(-1, 4), axis=1)) / np.linalg.norm(g_quat, axis=1)
+            parity = {"max_dpos": float(np.abs(g_pos - bo.pos.reshape(-1, 3)).max()),
+                      "max_datt": float((2.0 * np.arccos(np.clip(dq, -1.0, 1.0))).max()),
+                      "n_envs": int(pe), "steps": int(ps), "substeps": int(ps * K),
+                      "tolerance": {"pos_m": 1e-4, "att_rad": 1e-4},
+                      "oracle": "oracle/batch.py (FP64, pinned to the per-vehicle oracle by tests/test_oracle_batch.py) on the "
+                                "first %d envs of the timed swarm, same initial state and targets" % pe}
+            parity["ok"] = bool(parity["max_dpos"] <= 1e-4 and parity["max_datt"] <= 1e-4)
+    core.reset(pos0, action0=act0)
+    core.stats_reset()
 
     sampler = ClockSampler(local_rank)
     # ---- device-resident timing -------------------------------------------------------------
@@ -255,14 +333,8 @@ def run_ours(args):
     barrier()
     sampler.start()
     l0 = core.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    core.step(targets, args.steps)
-    ev1.record()
-    barrier()
+    ms_total, per_step = timed_steps(core, targets, args.steps, barrier, max_over_ranks, torch)
     launches = core.launch_count() - l0
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
     value = N * n_gpus * K * args.steps / (ms_total * 1e-3)
 
@@ -270,9 +342,9 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or min(args.steps, 48)
-        chunk = 16  # control steps per ds_rollout_host call (1 GiB of pinned targets at 4 Mi vehicles)
+        chunk = 16  # control steps per rollout call (1 GiB of pinned per-vehicle targets at 4 Mi vehicles)
         e2e_steps = max(chunk, (e2e_steps // chunk) * chunk)
-        # (1) pipelined rollout: targets of `chunk` control steps per call, H2D / D2H overlapped with the compute
+        # (1) headline: per-vehicle set-points [N][4] f32 every step, H2D / D2H overlapped with the compute
         h_roll = torch.from_numpy(tgt32).unsqueeze(0).repeat(chunk, 1, 1).contiguous().pin_memory()
         h_roll_done = torch.zeros((chunk, E), dtype=torch.uint8).pin_memory()
         core.rollout_host(h_roll, h_roll_done)
@@ -287,11 +359,34 @@ def run_ours(args):
         e2e = {"value": N * n_gpus * K * e2e_steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(N * 16 * n_gpus), "d2h_bytes_per_step": int(E * n_gpus),
                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "host_affinity": numa,
+               "h2d_gbs_per_gpu": N * 16 / (e2e_s / e2e_steps) / 1e9,
                "call": "ds_rollout_host (%d control steps per call): per step, pinned targets [N][4] f32 -> HBM on a copy "
-                       "stream, fused step, per-env done u8 -> pinned host; copies overlap the previous / next step's "
-                       "compute; synchronised at the end of each call" % chunk}
-        del h_roll, h_roll_done
-        # (2) strictly synchronous per-step call (copy, step, copy, sync) for comparison
+                       "stream in 8 MiB pieces, fused step, per-env done u8 -> pinned host; copies overlap the previous / next "
+                       "step's compute; synchronised at the end of each call" % chunk}
+        del h_roll
+        # (2) compact: the set-points the way the reference scripts pass them - a waypoint table resident on the device
+        # (here one hover row + the resident per-vehicle offsets) and ONE int32 index per vehicle and step from the host
+        tab = np.zeros((1, 10))
+        off = np.concatenate([tgt32[:, :3], np.zeros((N, 1), np.float32)], axis=1)
+        t_tab = core.targets_table(tab, offset=torch.from_numpy(off).to(dev))
+        h_wp = torch.zeros((chunk, N), dtype=torch.int32).pin_memory()
+        core.rollout_host_table(t_tab, h_wp, h_roll_done)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps // chunk):
+            core.rollout_host_table(t_tab, h_wp, h_roll_done)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        c_s = max_over_ranks(t1 - t0)
+        e2e["compact_targets"] = {"value": N * n_gpus * K * e2e_steps / c_s, "unit": UNIT, "steps": e2e_steps,
+                                  "ms_per_step": 1e3 * c_s / e2e_steps, "h2d_bytes_per_step": int(N * 4 * n_gpus),
+                                  "d2h_bytes_per_step": int(E * n_gpus),
+                                  "call": "ds_rollout_host_table: device-resident waypoint table + per-vehicle offsets, per step "
+                                          "one int32 waypoint index per vehicle from pinned host memory (fly_INDI.py:230-245 "
+                                          "passes TARGET_POS[wp_counters[j]]), per-env done u8 back"}
+        del h_wp, h_roll_done, t_tab
+        # (3) strictly synchronous per-step call (copy, step, copy, sync) for comparison
         h_tgt = torch.from_numpy(tgt32).pin_memory()
         h_done = torch.zeros((E,), dtype=torch.uint8).pin_memory()
         for _ in range(3):
@@ -307,7 +402,7 @@ def run_ours(args):
         sync_s = max_over_ranks(t1 - t0)
         e2e["per_step_sync"] = {"value": N * n_gpus * K * n_sync / sync_s, "unit": UNIT, "steps": n_sync,
                                 "ms_per_step": 1e3 * sync_s / n_sync, "call": "ds_step_host"}
-        # (3) the gym-style variant that also returns every vehicle's 22-float state vector to the host
+        # (4) the gym-style variant that also returns every vehicle's 22-float state vector to the host
         h_obs = torch.empty((N, L.DS_OBS_STRIDE), dtype=torch.float32).pin_memory()
         core.step_host(h_tgt, h_obs, h_done)
         barrier()
@@ -329,14 +424,15 @@ def run_ours(args):
     stats = allreduce_stats(core.stats(), device=dev)
     sane = (stats["non_finite"] == 0)
     core.close()
-    del d_tgt, d_vel, d_acc, targets
+    del d_tgt, d_vel, d_acc, targets, pos0, act0
 
-    # ---- secondary workloads: the single-type configs of BASELINE.json at the same vehicle count -------------
+    # ---- secondary workloads ------------------------------------------------------------------
+    peak, peak_src = hbm_peak()
     others = []
     if not args.no_others:
         from dronesim_b200.workloads import algorithmic_bytes_per_control_step, single_type
 
-        peak_o, _ = hbm_peak()
+        # (a) the single-type configs of BASELINE.json (configs[1], configs[2]) and the plain K=8 path, at the same vehicle count
         for name in ("quad_k8", "traj_quad", "hexa_circle"):
             models_o, K_o, flags_o, p0, a0, tab, wp0 = single_type(name, N, seed=0, env_offset=rank * N)
             c = SwarmCore(models_o, N, integrator="quat", aggregate_phy_steps=K_o, stats=True, device=local_rank, **flags_o)
@@ -345,84 +441,102 @@ def run_ours(args):
             tg = c.targets_table(tab)
             steps_o = max(20, args.steps // 2)
             c.step(tg, args.warmup)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            c.step(tg, steps_o)
-            e1.record()
-            barrier()
-            ms_o = max_over_ranks(e0.elapsed_time(e1)) / steps_o
+            ms_o_total, per_o = timed_steps(c, tg, steps_o, barrier, max_over_ranks, torch)
+            ms_o = ms_o_total / steps_o
             st_o = allreduce_stats(c.stats(), device=dev)
             n_u = 6 if "hexa" in models_o[0] else 4
             bytes_o = algorithmic_bytes_per_control_step(n_u, per_vehicle_targets=False)
             gbs = bytes_o * N / (ms_o * 1e-3) / 1e9
             others.append({"workload": name, "vehicles_per_gpu": N, "substeps_per_control_step": K_o, "flags": flags_o,
-                           "targets": "shared waypoint table + per-vehicle counter", "steps": steps_o, "ms_per_step": ms_o,
+                           "targets": "shared waypoint table + per-vehicle counter" + (
+                               " (the reference trajGenerator's 3-gate table, tests/golden/traj_3gates.npz)" if name == "traj_quad" else ""),
+                           "steps": steps_o, "ms_per_step": ms_o, "per_step": spread(per_o),
                            "value": N * n_gpus * K_o / (ms_o * 1e-3), "unit": UNIT,
                            "control_steps_per_s": N * n_gpus / (ms_o * 1e-3),
-                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_o, "unit": "GB/s", "frac": gbs / peak_o,
+                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                         "algorithmic_bytes_per_vehicle_control_step": bytes_o},
                            "sane": st_o["non_finite"] == 0})
             sane = sane and st_o["non_finite"] == 0
             c.close()
             del tg
+        # (b) BASELINE configs[4]: the 1M-64M sweep of the headline swarm on one GPU (single-GPU runs only: 8 GB of
+        # state + 5 GB of host arrays per rank at 64 Mi vehicles)
+        if world == 1 and not args.no_sweep:
+            for envs_s in (65536, 1048576, 4194304):
+                if envs_s == E:
+                    continue
+                m_s, K_s, f_s, p0, a0, tg_np = hetero16(envs_s, seed=0, dtype=np.float32)
+                c = SwarmCore(m_s, envs_s, integrator="quat", aggregate_phy_steps=K_s, stats=True, device=local_rank, **f_s)
+                c.reset(p0, action0=a0)
+                del p0, a0
+                tg = c.targets_per_vehicle(torch.from_numpy(tg_np).to(dev))
+                del tg_np
+                steps_s = 40 if envs_s <= 1048576 else 12
+                c.step(tg, 5)
+                ms_s_total, per_s = timed_steps(c, tg, steps_s, barrier, max_over_ranks, torch)
+                ms_s = ms_s_total / steps_s
+                st_s = c.stats()
+                n_s = envs_s * DRONES
+                others.append({"workload": "hetero16 sweep point (BASELINE configs[4])", "vehicles_per_gpu": n_s,
+                               "substeps_per_control_step": K_s, "steps": steps_s, "ms_per_step": ms_s, "per_step": spread(per_s),
+                               "value": n_s * K_s / (ms_s * 1e-3), "unit": UNIT, "resident_state_gb": n_s * 120 / 1e9,
+                               "sane": st_s["non_finite"] == 0})
+                sane = sane and st_s["non_finite"] == 0
+                c.close()
+                del tg
 
     # ---- rooflines ---------------------------------------------------------------------------
-    peak, peak_src = hbm_peak()
+    # The kernel is NOT bound by HBM: its binding limits are FP32 execution and instruction issue.
+    # `roofline` reports the FP32 one on EXECUTED FLOP (ncu, per SASS opcode incl. the packed FFMA2 / FMUL2 / FADD2) against
+    # the FFMA rate measured live on this GPU; the HBM and issue fractions sit beside it.
     bytes_per_launch = hetero16_bytes_per_control_step() * N
     hbm_achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    hbm = {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": bytes_per_launch,
+           "algorithmic_bytes_per_vehicle_control_step": hetero16_bytes_per_control_step()}
+    kernel_name = "ds_step_kernel<QUAT, DW=symmetric16, NU6, WARPSYNC, FUSED, FX=ground+drag, EXT=off, mixed types, CoM offsets>"
     roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": "ds_step_kernel<QUAT, DW=symmetric16, NU6, WARPSYNC, FUSED, FX=ground+drag, EXT=off>",
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "algorithmic_bytes_per_vehicle_control_step": hetero16_bytes_per_control_step()}
-    prof = os.path.join(ROOT, "profiles", "roofline_inputs.json")
-    fp32 = None
-    if os.path.isfile(prof):  # ncu-derived per-launch constants (traffic, executed FP32 instructions), see DESIGN.md
-        try:
-            with open(prof) as f:
-                pin = json.load(f)
-            if pin.get("vehicles_per_launch"):
-                scale = N / float(pin["vehicles_per_launch"])
-                if pin.get("dram_bytes_per_launch"):
-                    roofline["traffic"] = pin["dram_bytes_per_launch"] * scale
-                if pin.get("fp32_flop_per_launch"):
-                    # algorithmic FLOP: the FP32 operations of the straightforward formulation (every ordered downwash
-                    # pair evaluated, as the reference's double loop does), counted once by ncu on the r1f build
-                    fl = pin["fp32_flop_per_launch"] * scale
-                    fp32 = {"flop_per_launch": fl, "source": pin.get("source", "profiles/")}
-                    if pin.get("fp32_flop_executed_per_launch"):
-                        fp32["flop_executed_per_launch"] = pin["fp32_flop_executed_per_launch"] * scale
-                if pin.get("warp_inst_per_launch"):
-                    # the limit that actually binds this kernel: warp instructions issued per second against
-                    # SMs x 4 schedulers x SM clock (one instruction per scheduler per cycle)
-                    sm = float(clocks.get("sm_mhz") or 0.0) * 1e6
-                    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-                    wi = pin["warp_inst_per_launch"] * scale
-                    if sm > 0:
-                        roofline["issue"] = {"warp_inst_per_launch": wi, "achieved_ginst_s": wi / (ms_per_step * 1e-3) / 1e9,
-                                             "peak_ginst_s": sms * 4 * sm / 1e9,
-                                             "frac": wi / (ms_per_step * 1e-3) / (sms * 4 * sm),
-                                             "source": pin.get("source_inst", pin.get("source", "profiles/"))}
-        except Exception:
-            pass
+                "traffic": None, "peak_source": peak_src, "kernel": kernel_name, "hbm": hbm}
+    fp32_peak = None
     if rank == 0:
         import ctypes as C
 
         pk = C.c_double(0.0)
         if L.lib().ds_debug_fp32_peak(local_rank, C.byref(pk)) == 0 and pk.value > 0:
-            fp32 = fp32 or {}
-            fp32["peak_tflops_measured"] = pk.value
-            if "flop_per_launch" in fp32:
-                fp32["achieved_tflops"] = fp32["flop_per_launch"] / (ms_per_step * 1e-3) / 1e12
-                fp32["frac"] = fp32["achieved_tflops"] / pk.value
-    if fp32:
-        roofline["fp32"] = fp32
+            fp32_peak = pk.value
+    prof = os.path.join(ROOT, "profiles", "roofline_inputs.json")
+    if os.path.isfile(prof):
+        try:
+            with open(prof) as f:
+                pin = json.load(f)
+            fresh = pin.get("source_hash") == L.source_hash()
+            roofline["inputs"] = {"file": "profiles/roofline_inputs.json", "report": pin.get("report"),
+                                  "source_hash": pin.get("source_hash"), "built_source_hash": L.source_hash(), "fresh": fresh}
+            if fresh and pin.get("vehicles_per_launch"):
+                scale = N / float(pin["vehicles_per_launch"])
+                roofline["traffic"] = pin["dram_bytes_per_launch"] * scale
+                flop = pin["fp32_flop_executed_per_launch"] * scale
+                wi = pin["warp_inst_per_launch"] * scale
+                sm = float(clocks.get("sm_mhz") or 0.0) * 1e6
+                sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                if sm > 0:
+                    roofline["issue"] = {"warp_inst_per_launch": wi, "achieved_ginst_s": wi / (ms_per_step * 1e-3) / 1e9,
+                                         "peak_ginst_s": sms * 4 * sm / 1e9, "frac": wi / (ms_per_step * 1e-3) / (sms * 4 * sm),
+                                         "packed_fp32_share_of_fp32_inst": pin["packed_fp32_warp_inst_per_launch"] / max(1.0, pin["fp32_warp_inst_per_launch"])}
+                if fp32_peak:
+                    tf = flop / (ms_per_step * 1e-3) / 1e12
+                    roofline.update({"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                                     "peak_source": "FFMA micro-benchmark run live on this GPU (ds_debug_fp32_peak; MEASURED_PEAKS.json "
+                                                    "carries no FP32 CUDA-core figure); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
+                                     "flop_executed_per_launch": flop,
+                                     "flop_source": "ncu per-opcode predicated-on thread instructions (tools/roofline_inputs.py)"})
+        except Exception as e:
+            roofline["inputs"] = {"error": repr(e)[:200]}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_bench import time_oracle
+        from oracle.cpu_bench import reference_available
 
         cores = os.cpu_count() or 1
         try:  # the GPU-side NUMA binding must not shrink the CPU arm: its workers inherit this process's affinity
@@ -430,27 +544,30 @@ def run_ours(args):
             cores = len(os.sched_getaffinity(0))
         except Exception:
             pass
-        n_cpu = args.cpu_steps
-        if n_cpu <= 0:  # bounded sample: ~12 s of CPU work, sized from a 2-step calibration
-            cal = time_oracle(steps=2, warmup=1, workers=cores, envs_per_worker=1)
-            n_cpu = int(min(600, max(3, round(12.0 / max(cal["seconds"] / 2.0, 1e-3)))))
-        r = time_oracle(steps=n_cpu, warmup=1, workers=cores, envs_per_worker=1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
-               "seconds": r["seconds"]}
+        kinds = (["reference-executed"] if reference_available() else []) + ["port", "vectorised"]
+        arms = cpu_arms(kinds, cores)
+        main_kind = "reference-executed" if "reference-executed" in arms and arms["reference-executed"].get("value") else "port"
+        cpu = dict(arms[main_kind])
+        cpu["kind"] = "reference" if main_kind == "reference-executed" else "port"
+        cpu["detail"] = main_kind
+        cpu["vectorised"] = arms.get("vectorised")
+        if main_kind != "port":
+            cpu["port"] = arms.get("port")
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(E, n_gpus),
+            "ms_per_step": ms_per_step, "per_step": spread(per_step), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(E, n_gpus),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "parity_check": parity,
             "control_steps_per_s": N * n_gpus * args.steps / (ms_total * 1e-3),
-            "rollout_stats": stats, "sane": bool(sane), "other_workloads": others,
+            "rollout_stats": stats, "sane": bool(sane and (parity is None or parity["ok"])), "other_workloads": others,
         }
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
-    return 0 if sane else 3
+    return 0 if (sane and (parity is None or rank != 0 or parity["ok"])) else 3
 
 
 def _emit(line: dict):

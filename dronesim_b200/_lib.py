@@ -163,6 +163,21 @@ def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: 
     return out_path
 
 
+def source_hash() -> str:
+    """sha256 over everything the built kernels are a function of (CUDA sources, the C header, the nvcc flags).
+    ``profiles/roofline_inputs.json`` is stamped with it; ``bench.py`` refuses ncu-derived constants measured on other sources."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(INCLUDE, "dronesim_b200.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 _lib = None
 
 

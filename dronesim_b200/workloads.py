@@ -25,11 +25,12 @@ import numpy as np
 HETERO16_MODELS = ["robobee", "tello"] * 4 + ["hexa_6DOF"] * 8
 
 
-def hetero16(n_envs: int, seed: int = 0, env_offset: int = 0):
+def hetero16(n_envs: int, seed: int = 0, env_offset: int = 0, dtype=np.float64):
     """(models, K, flags, pos0[E,16,3], action0[E,16,6], targets[E*16,4]) of the heterogeneous swarm.
 
     The per-env random offsets are a pure function of (seed, global env index), so any sharding of
-    the envs over ranks reproduces the same swarm."""
+    the envs over ranks reproduces the same swarm.  ``dtype=np.float32`` halves the host memory of the 64 Mi-vehicle
+    sweep point (the core converts to float32 anyway)."""
     D = 16
     slot = np.arange(D)
     base = np.stack([1.0 * (slot % 4), 1.0 * (slot // 4), 2.0 + 0.25 * slot], axis=1)  # [16,3]
@@ -37,11 +38,12 @@ def hetero16(n_envs: int, seed: int = 0, env_offset: int = 0):
     e = (np.arange(n_envs, dtype=np.uint64) + np.uint64(env_offset))[:, None, None]
     idx = (e * np.uint64(D) + slot.astype(np.uint64)[None, :, None]) * np.uint64(3) + np.arange(3, dtype=np.uint64)[None, None, :]
     noise = (_hash01(idx, seed) - 0.5) * 0.04
-    pos0 = base[None, :, :] + noise
-    action0 = np.zeros((n_envs, D, 6))
+    pos0 = (base[None, :, :] + noise).astype(dtype)
+    del noise, idx
+    action0 = np.zeros((n_envs, D, 6), dtype=dtype)
     action0[:, :8, :4] = 0.45
     action0[:, 8:, :] = 0.45
-    tgt = np.concatenate([pos0.reshape(-1, 3), np.zeros((n_envs * D, 1))], axis=1)
+    tgt = np.concatenate([pos0.reshape(-1, 3), np.zeros((n_envs * D, 1), dtype=dtype)], axis=1)
     flags = dict(ground=True, drag=True, downwash=True)
     return HETERO16_MODELS, 8, flags, pos0, action0, tgt
 
@@ -83,12 +85,21 @@ def circle_table(num_wp: int = 1440, radius: float = 1.2, z: float = 0.6) -> np.
     return tab
 
 
+def reference_trajectory_table() -> np.ndarray:
+    """[1200, 10] = pos3 vel3 acc3 yaw: the table the reference's ``trajGenerator`` returns for the three gates of
+    fly_INDI_TrajectoryTrack.py:133-160, generated by executing the reference (tests/golden/make_golden.py::traj_fixture)."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "traj_3gates.npz")
+    return np.array(np.load(path)["table"], dtype=np.float64)
+
+
 def single_type(name: str, n_envs: int, seed: int = 0, env_offset: int = 0):
     """(models, K, flags, pos0[E,1,3], action0[E,1,6], table[num_wp,10], wp0[E]) of
 
-    ``"traj_quad"``  configs[1]: robobee tracking a waypoint table, K = 2 (96 Hz control), no add-ons.  The
-                     table is a 1200-row stand-in with the shape of the reference's 3-gate trajectory
-                     (the exact trajGenerator table lives in tests/golden/traj_3gates.npz);
+    ``"traj_quad"``  configs[1]: robobee tracking the reference's own 3-gate trajectory (the 1200-row table its
+                     trajGenerator produces for fly_INDI_TrajectoryTrack.py:133-160, frozen in
+                     tests/golden/traj_3gates.npz), K = 2 (96 Hz control), no add-ons;
     ``"hexa_circle"`` configs[2]: hexa_6DOF on the fly_hexa_6DOF.py circle, K = 2, ground effect + drag;
     ``"quad_k8"``    robobee hover-table, K = 8, no add-ons (the plain dynamics + INDI path of configs[4]).
     """
@@ -97,13 +108,7 @@ def single_type(name: str, n_envs: int, seed: int = 0, env_offset: int = 0):
     noise = (_hash01(idx, seed) - 0.5) * 0.1  # U(-0.05, 0.05)
     if name == "traj_quad":
         models, K, flags = ["robobee"], 2, dict(ground=False, drag=False, downwash=False)
-        t = np.linspace(0.0, 1.0, 1200)
-        tab = np.zeros((1200, 10))
-        tab[:, 0] = -3.0 + 6.0 * t
-        tab[:, 1] = np.sin(np.pi * t)
-        tab[:, 2] = 2.0 + 3.0 * np.sin(np.pi * t)
-        tab[:, 3:6] = np.gradient(tab[:, 0:3], 1.0 / 96.0, axis=0)
-        tab[:, 6:9] = np.gradient(tab[:, 3:6], 1.0 / 96.0, axis=0)
+        tab = reference_trajectory_table()
         base, cmd0 = np.array([-3.0, 0.0, 2.0]), 0.4
     elif name == "hexa_circle":
         models, K, flags = ["hexa_6DOF"], 2, dict(ground=True, drag=True, downwash=False)

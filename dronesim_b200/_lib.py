@@ -24,7 +24,7 @@ DS_NUM_STATS = 16
 
 DS_OK, DS_ERR_INVALID, DS_ERR_CUDA, DS_ERR_STATE, DS_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 DS_INTEG_QUAT, DS_INTEG_RPY = 0, 1
-DS_FLAG_GROUND, DS_FLAG_DRAG, DS_FLAG_DOWNWASH, DS_FLAG_STATS, DS_FLAG_DW_ORDERED_PAIRS, DS_FLAG_TYPES_IN_SMEM = 1, 2, 4, 8, 16, 32
+DS_FLAG_GROUND, DS_FLAG_DRAG, DS_FLAG_DOWNWASH, DS_FLAG_STATS, DS_FLAG_DW_ORDERED_PAIRS, DS_FLAG_TYPES_IN_SMEM, DS_FLAG_GROUND_PLANE = 1, 2, 4, 8, 16, 32, 64
 DS_LAW_QUAD, DS_LAW_6DOF = 0, 1
 DS_DONE_GOAL, DS_DONE_FLOOR, DS_DONE_TIME = 1, 2, 4
 DS_ORDER_PHYSICS_THEN_CONTROL, DS_ORDER_CONTROL_THEN_PHYSICS = 0, 1
@@ -41,6 +41,7 @@ class ds_config(C.Structure):
         ("max_steps", C.c_int32), ("env_offset", C.c_int32),
         ("motor_tau", C.c_float), ("acc_filter_hz", C.c_float), ("reward_mode", C.c_int32),
         ("noise_force_sigma", C.c_float), ("noise_torque_sigma", C.c_float), ("noise_seed", C.c_uint64),
+        ("ground_plane_z", C.c_float), ("reserved0", C.c_int32),
     ]
 
 

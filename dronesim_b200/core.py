@@ -93,7 +93,7 @@ class SwarmCore:
                  freq: float = 240.0, aggregate_phy_steps: int = 1, neighbourhood_radius: float = math.inf,
                  gravity: float = 9.8, goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0,
                  device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None, dw_ordered_pairs: bool = False,
-                 types_in_smem: bool = False,
+                 types_in_smem: bool = False, ground_plane_z: Optional[float] = None,
                  motor_tau: float = 0.0, acc_filter_hz: float = 0.0, reward_mode: int = 0,
                  noise_force_sigma: float = 0.0, noise_torque_sigma: float = 0.0, noise_seed: int = 0):
         lib = L.lib()
@@ -115,7 +115,9 @@ class SwarmCore:
         cfg.flags = ((L.DS_FLAG_GROUND if ground else 0) | (L.DS_FLAG_DRAG if drag else 0)
                      | (L.DS_FLAG_DOWNWASH if downwash else 0) | (L.DS_FLAG_STATS if stats else 0)
                      | (L.DS_FLAG_DW_ORDERED_PAIRS if dw_ordered_pairs else 0)
-                     | (L.DS_FLAG_TYPES_IN_SMEM if types_in_smem else 0))
+                     | (L.DS_FLAG_TYPES_IN_SMEM if types_in_smem else 0)
+                     | (L.DS_FLAG_GROUND_PLANE if ground_plane_z is not None else 0))
+        cfg.ground_plane_z = float(ground_plane_z) if ground_plane_z is not None else 0.0
         cfg.device, cfg.sim_freq, cfg.gravity = self.device_index, float(freq), float(gravity)
         cfg.neighbourhood_radius = float(neighbourhood_radius)
         if goal is not None:

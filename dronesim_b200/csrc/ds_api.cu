@@ -457,7 +457,8 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.seed_lo = (uint32_t)(h->cfg.noise_seed & 0xffffffffu); a.seed_hi = (uint32_t)(h->cfg.noise_seed >> 32);
   a.veh0 = (uint32_t)((int64_t)h->cfg.env_offset * h->cfg.drones_per_env);
   a.step0 = (uint32_t)h->step_counter;
-  a.flags = h->cfg.flags & 0xFu;
+  a.flags = h->cfg.flags & (0xFu | DS_FLAG_GROUND_PLANE);
+  a.floor_z = h->cfg.ground_plane_z;
   a.dt = 1.0f / h->cfg.sim_freq;
   a.gravity = h->cfg.gravity;
   {
@@ -565,6 +566,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
         if (rc != DS_OK) return rc;
       }
     }
+    CK(cudaGetLastError());
     return DS_OK;
   }
   for (int i = 0; i < n_control_steps; ++i) {
@@ -596,8 +598,22 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   return DS_OK;
 }
 
+// true if p is NULL or memory a kernel on the handle's device can write (device / managed / registered host)
+static bool device_writable(const ds_handle* h, const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type == cudaMemoryTypeDevice) return at.device == h->cfg.device;
+  return at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int ds_set_env_outputs(ds_handle* h, uint8_t* done_env, float* reward_env) {
   if (!h) return DS_ERR_INVALID;
+  ON_DEVICE(h);
+  // the step kernel will write n_envs entries through these pointers on every following step: refuse anything that is
+  // not device-accessible memory (a host pointer here would fault inside the kernel, far from the cause)
+  if (!device_writable(h, done_env) || !device_writable(h, reward_env)) return DS_ERR_INVALID;
+  if (((uintptr_t)reward_env & 3u) != 0) return DS_ERR_INVALID;
   h->env_done_out = done_env;
   h->env_reward_out = reward_env;
   return DS_OK;

@@ -123,6 +123,7 @@ struct DsArgs {
   int store_act;    // physics stores the clipped action to s_a0/s_a1
   float dt;         // TIMESTEP
   float gravity;
+  float floor_z;    // DS_FLAG_GROUND_PLANE: hard floor for the centre of mass (run-time-flag kernel variants, a.flags bit 6)
   float dtg;        // TIMESTEP * gravity
   float qh;         // 0.25 TIMESTEP^2: (half angle)^2 of a substep = qh |w|^2
   float qk[4];      // TIMESTEP x Taylor coefficients of 0.5 sin(h)/h in h^2 (ds_quat_step)

@@ -464,6 +464,9 @@ __device__ __forceinline__ void ds_physics(const DsArgs& a, const DsTypeDev& tp,
     }
     cxy = ds_fma(uxy, dt, cxy);
     cz = ds_fma(uz, dt, cz);
+    if (FX < 0 && (a.flags & 64u)) {  // DS_FLAG_GROUND_PLANE: inelastic, frictionless stop (plane.urdf, BaseAviary.py:679-680)
+      if (cz < a.floor_z) { cz = a.floor_z; uz = fmaxf(uz, 0.f); }
+    }
     if (INTEG == 1) {
       roll = fmaf(dt, f2_lo(wxy), roll); pitch = fmaf(dt, f2_hi(wxy), pitch); yaw = fmaf(dt, wz, yaw);
       float4 q = ds_quat_from_euler(roll, pitch, yaw);  // :1817

@@ -64,7 +64,8 @@ static void launch2(bool warpsync, const DsArgs& a, const DsTypeDev* homo, int g
   // EXT: motor model / angular-acceleration filter (extensions beyond the reference; quaternion integrator only)
   if (a.ext) { launch3<DW, NU6, -1, true>(warpsync, a, homo, grid, st); return; }
 #endif
-  if (DW != 0 && (a.flags & 3u) == 3u) launch3<DW, NU6, 3, false>(warpsync, a, homo, grid, st);
+  // (the ground plane is a run-time flag as well: it rides in the FX = -1 variants only)
+  if (DW != 0 && (a.flags & 3u) == 3u && !(a.flags & 64u)) launch3<DW, NU6, 3, false>(warpsync, a, homo, grid, st);
   else launch3<DW, NU6, -1, false>(warpsync, a, homo, grid, st);
 }
 

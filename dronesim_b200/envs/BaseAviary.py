@@ -56,7 +56,8 @@ class BaseAviary:
                  initial_xyzs=None, initial_vels=None, initial_rpys=None, physics: Physics = Physics.PYB, freq: int = 240,
                  aggregate_phy_steps: int = 1, gui=False, record=False, obstacles=False, user_debug_gui=False,
                  vision_attributes=False, dynamics_attributes=False, *, num_envs: int = 1, device: int = 0,
-                 goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0):
+                 goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0, ground_plane: bool = False,
+                 auto_reset: bool = False):
         from ..core import SwarmCore
 
         #### Constants (BaseAviary.py:182-187)
@@ -102,7 +103,11 @@ class BaseAviary:
         self._core = SwarmCore(self.drones, self.NUM_ENVS, integrator=integ, ground=gnd, drag=drag, downwash=dw,
                                freq=float(freq), aggregate_phy_steps=int(aggregate_phy_steps),
                                neighbourhood_radius=float(neighbourhood_radius), gravity=self.G, device=device, goal=goal,
-                               goal_radius=goal_radius, z_min=z_min, max_steps=max_steps)
+                               goal_radius=goal_radius, z_min=z_min, max_steps=max_steps,
+                               ground_plane_z=(0.0 if ground_plane else None))
+        #### Batched extension: envs whose ``done`` fired are reset on the device right after the step that reports it
+        #### (BaseAviary.reset per environment, BaseAviary.py:406-424), with no host round trip
+        self.AUTO_RESET = bool(auto_reset)
         self.CLIENT = -1  # no PyBullet client
         self.DRONE_IDS = np.arange(1, num_drones + 1)
         self._n_u = [d.INDI_ACTUATOR_NR for d in self.drones]
@@ -128,7 +133,14 @@ class BaseAviary:
         done = self._computeDone()
         info = self._computeInfo()
         self.step_counter = self._core.step_counter  # += AGGR_PHY_STEPS (:554)
+        if self.AUTO_RESET:
+            self.reset_envs(self._done_dev)  # the returned obs / done describe the finished episode's last step
         return obs, reward, done, info
+
+    def reset_envs(self, mask):
+        """``reset()`` for the environments with ``mask[e] != 0`` only ([NUM_ENVS] bool / uint8, device tensor or array),
+        on the device and without a host synchronisation; the others keep flying."""
+        self._core.reset_envs(mask, self._init_dev[0], rpy0=self._init_dev[1], vel0=self._init_dev[2])
 
     def _advance(self, action):
         """``_preprocessAction`` + the AGGR_PHY_STEPS substeps (BaseAviary.py:507-545), one kernel launch.
@@ -180,6 +192,11 @@ class BaseAviary:
             vel0 = bc(vel0)
         self._core.reset(bc(self.INIT_XYZS), rpy0=bc(self.INIT_RPYS), vel0=vel0)
         self.last_clipped_action = {str(i): np.zeros(self._n_u[i]) for i in range(D)}
+        import torch
+
+        dev = self._core.device  # the initial poses stay resident for masked resets (reset_envs / auto_reset)
+        f = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev).reshape(E * D, 3)  # noqa: E731
+        self._init_dev = (f(bc(self.INIT_XYZS)), f(bc(self.INIT_RPYS)), f(vel0))
 
     def _pack_action(self, action, width: int = 6):
         """dict {str(i): [<= width]} (reference form, one env) or array/tensor [E, D, <= width] -> device [N, width]."""

@@ -35,7 +35,8 @@ def main(argv=None):
     INIT_RPYS = np.array([[0.0, 0.0, 0.0]])
     env = CtrlAviary(drone_model=[ARGS.drone], num_drones=1, initial_xyzs=INIT_XYZS, initial_rpys=INIT_RPYS,
                      physics=Physics(ARGS.physics), neighbourhood_radius=10, freq=ARGS.simulation_freq_hz,
-                     aggregate_phy_steps=AGGR_PHY_STEPS, num_envs=ARGS.num_envs)
+                     aggregate_phy_steps=AGGR_PHY_STEPS, num_envs=ARGS.num_envs,
+                     ground_plane=(ARGS.physics != "dyn"))  # the PyBullet world has a floor (BaseAviary.py:679-680)
     ctrl = [INDIControl(drone_model=ARGS.drone, num_envs=ARGS.num_envs)]
     NUM_WP = ARGS.control_freq_hz * 15                                    # :151-167
     TARGET_RPYS = np.array([[0, 0, 0.4 + i / 200] for i in range(NUM_WP)])

@@ -56,7 +56,10 @@ enum { DS_FLAG_GROUND = 1u, DS_FLAG_DRAG = 2u, DS_FLAG_DOWNWASH = 4u, DS_FLAG_ST
        DS_FLAG_DW_ORDERED_PAIRS = 16u,
        /* diagnostics: a single-type swarm runs the mixed-swarm kernel variant (per-type tables in shared memory) instead
         * of the homogeneous one (its type table in the kernel parameters); results are bit-identical */
-       DS_FLAG_TYPES_IN_SMEM = 32u };
+       DS_FLAG_TYPES_IN_SMEM = 32u,
+       /* the ground plane of the reference's PyBullet world as a hard floor at ds_config.ground_plane_z (off by default:
+        * the reference's explicit-dynamics formulas have no contact) */
+       DS_FLAG_GROUND_PLANE = 64u };
 
 /* control laws: which reference controller class flies the type */
 enum { DS_LAW_QUAD = 0 /* INDIControl.py */, DS_LAW_6DOF = 1 /* INDIControl_6DOF.py */ };
@@ -104,6 +107,12 @@ typedef struct ds_config {
   float noise_force_sigma;
   float noise_torque_sigma;
   uint64_t noise_seed;
+  /* DS_FLAG_GROUND_PLANE: the plane the reference loads under the aviary (plane.urdf, BaseAviary.py:679-680), as an
+   * inelastic frictionless stop: after every substep a centre of mass below ground_plane_z is put back on it and loses its
+   * downward velocity.  A stand-in for Bullet's contact solver, enough for the take-off phases of the example scripts
+   * (fly_INDI.py starts with all-zero controller commands and touches down before it lifts off). */
+  float ground_plane_z;
+  int32_t reserved0;
 } ds_config;
 
 /* Per-type constants.  Field sources: BaseAviary._parseURDFParameters (BaseAviary.py:2041-2140),

@@ -219,8 +219,10 @@ def substep_rpy(pp, dt, pos, quat, rpy, vel, rates, F, tau, R):
     return pos, quat, rpy, vel, rates
 
 
-def substep_quat(pp, dt, pos, quat, vel, w, F, tau, R):
-    """R8: rigid body about the composite centre of mass, semi-implicit Euler."""
+def substep_quat(pp, dt, pos, quat, vel, w, F, tau, R, floor_z=None):
+    """R8: rigid body about the composite centre of mass, semi-implicit Euler.
+    ``floor_z``: the ground plane of the PyBullet world (plane.urdf, BaseAviary.py:679-680) as an inelastic frictionless
+    stop for the centre of mass (a stand-in for Bullet's contact; off by default)."""
     rc_w = R.dot(pp.r_com)
     c = pos + rc_w
     vc = vel + R.dot(np.cross(w, pp.r_com))
@@ -229,6 +231,9 @@ def substep_quat(pp, dt, pos, quat, vel, w, F, tau, R):
     vc = vc + dt * acc
     w = w + dt * wdot
     c = c + dt * vc
+    if floor_z is not None and c[2] < floor_z:
+        c[2] = floor_z
+        vc[2] = max(vc[2], 0.0)
     quat = quat_mul(quat, quat_exp(w, dt))
     quat = quat / math.sqrt(float(quat.dot(quat)))
     R2 = p.rotmat(quat)

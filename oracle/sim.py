@@ -56,6 +56,7 @@ class OracleSwarm:
         # rotor noise: the reference's N(0, 0.01) / N(0, 0.001) draws, from a counter-based source (oracle/noise.py)
         self.noise_f, self.noise_m = float(noise_force_sigma), float(noise_torque_sigma)
         self.noise_seed, self.env_offset = int(noise_seed), int(env_offset)
+        self.floor_z = None  # ground plane (DS_FLAG_GROUND_PLANE), quaternion integrator only
         self.goal = None
         self.goal_radius = 0.3
         self.z_min = None
@@ -149,7 +150,7 @@ class OracleSwarm:
                                                   self.vel[e, d], self.rates[e, d], F, tau, R))
                     else:
                         ps, q, v, w = od.substep_quat(pp, dt, snap_pos[d], self.quat[e, d], self.vel[e, d],
-                                                      self.rates[e, d], F, tau, R)
+                                                      self.rates[e, d], F, tau, R, floor_z=self.floor_z)
                         new.append((ps, q, np.array(p.getEulerFromQuaternion(q)), v, w))
                 for d in range(self.D):
                     self.pos[e, d], self.quat[e, d], self.rpy[e, d], self.vel[e, d], self.rates[e, d] = new[d]

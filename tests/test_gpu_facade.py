@@ -221,3 +221,96 @@ def test_example_script_runs_like_the_reference_example():
     assert np.isfinite(p1).all() and -0.5 < p1[2] < 0.5 and 0.2 < p1[1] < 0.9
     p4 = mod.main(["--duration_sec", "1", "--num_envs", "4"])
     np.testing.assert_allclose(p4, p1, atol=1e-6)
+
+
+def _load_example(name):
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "examples", name + ".py")
+    spec = importlib.util.spec_from_file_location(name + "_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_example_trajectory_track_reaches_the_final_gate():
+    """examples/fly_INDI_TrajectoryTrack.py (BASELINE configs[1]): the robobee follows the reference trajGenerator's table
+    through the three gates and stops within 0.3 m of the last one (:249-250); 4 envs fly the same flight."""
+    _need_gpu()
+    mod = _load_example("fly_INDI_TrajectoryTrack")
+    o1 = mod.main([])
+    # the law leads the 12.5 s table (velocity / acceleration feed-forward): the 0.3 m stop fires after ~8.5 s
+    assert o1["reached_final_gate_at_s"] is not None and 6.0 < o1["reached_final_gate_at_s"] < 12.5
+    assert o1["rms_tracking_error_m"] < 0.4
+    assert np.linalg.norm(np.array(o1["final_position"]) - np.array([3.0, 0.0, 2.0])) < 0.35
+    o4 = mod.main(["--num_envs", "4"])
+    assert o4["reached_final_gate_at_s"] == o1["reached_final_gate_at_s"]
+    np.testing.assert_allclose(o4["final_position"], o1["final_position"], atol=1e-6)
+
+
+def test_example_hexa_6dof_circle():
+    """examples/fly_hexa_6DOF.py (BASELINE configs[2]): 6-DOF law + WLS, ground effect + drag + downwash flags, level flight."""
+    _need_gpu()
+    mod = _load_example("fly_hexa_6DOF")
+    o = mod.main(["--duration_sec", "6"])
+    # the reference gains trail the 1 m/s circle set-point by most of a metre (recorded in profiles/hover_tracking_r02.json)
+    assert o["rms_tracking_error_m_after_2s"] < 1.2
+    assert o["max_abs_roll_pitch_rad_after_2s"] < 0.08   # the tilted-rotor hexa translates without banking
+    assert abs(o["final_position"][2] - 0.6) < 0.1
+    o3 = mod.main(["--duration_sec", "3", "--num_envs", "3"])
+    assert np.isfinite(o3["final_position"]).all()
+
+
+def test_example_velocity_commands():
+    """examples/fly_INDI_velocity.py: five tellos reach the commanded velocity (2 % of the speed limit along (1,1,1))."""
+    _need_gpu()
+    mod = _load_example("fly_INDI_velocity")
+    o = mod.main(["--duration_sec", "6"])
+    assert o["final_velocity_error_max"] < 0.02
+    assert all(d > 0.2 for d in o["displacement_mean"])
+
+
+def test_ground_plane_and_auto_reset():
+    """DS_FLAG_GROUND_PLANE against the oracle's floor, and the batched auto-reset of finished envs."""
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.envs.CtrlAviary import CtrlAviary, Physics
+
+    # (a) a robobee dropped from 0.4 m with the controller restarting from cmd = 0 touches down, rests, lifts off
+    vt = load_vehicle("robobee")
+    core = SwarmCore([vt], 2, aggregate_phy_steps=5, ground_plane_z=0.0)
+    orc = OracleSwarm([vt], 2, integrator="quat", composite=True, aggregate_phy_steps=5)
+    orc.floor_z = 0.0
+    pos0 = np.array([[0.0, 0.0, 0.4], [0.3, 0.0, 0.2]])
+    core.reset(pos0)
+    orc.reset(pos0)
+    tgt = core.targets_per_vehicle(np.array([[0.0, 0.0, 0.5, 0.0], [0.3, 0.0, 0.5, 0.0]]))
+    act = np.zeros((2, 1, 6))
+    zmin = 1.0
+    for step in range(96):  # 2 s
+        core.step(tgt, 1)
+        orc.physics_step(act)
+        act = orc.control_step(np.array([[0.0, 0.0, 0.5], [0.3, 0.0, 0.5]]).reshape(2, 1, 3))
+        zmin = min(zmin, float(core.views()["pos"][:, 2].min()))
+    assert zmin >= -1e-6 and zmin < 1e-3                       # it did reach the floor and never went through it
+    np.testing.assert_allclose(core.views()["pos"].cpu().numpy(), orc.pos.reshape(2, 3), atol=2e-4)
+    assert core.views()["pos"][:, 2].min() > 0.3               # and took off again towards the set-point
+    core.close()
+    # (b) auto-reset: envs whose done fires are put back to their initial pose on the device, the others keep flying
+    E = 6
+    xyz = np.zeros((E, 1, 3))
+    xyz[:, 0, 2] = [1.0, 1.0, 0.05, 1.0, 0.05, 1.0]
+    env = CtrlAviary(drone_model=["robobee"], num_drones=1, initial_xyzs=xyz, physics=Physics.PYB, aggregate_phy_steps=4,
+                     num_envs=E, z_min=0.02, auto_reset=True)
+    env.reset()
+    a = np.zeros((E, 1, 6), dtype=np.float32)
+    saw_done = np.zeros(E, dtype=bool)
+    for _ in range(12):
+        obs, rew, done, info = env.step(a)
+        saw_done |= done.cpu().numpy()
+    assert saw_done[[2, 4]].all() and not saw_done[[0, 1, 3, 5]].any()
+    z = env.state_tensor()[:, 0, 2].cpu().numpy()
+    assert (z[[2, 4]] > 0.0).all() and (z[[2, 4]] <= 0.05 + 1e-6).all()    # restarted from 0.05 m, still falling from there
+    assert (z[[0, 1, 3, 5]] < 0.95).all()                                 # never reset: 48 substeps of free fall from 1 m
+    env.close()

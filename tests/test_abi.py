@@ -102,3 +102,12 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_graft_entry_build_runs_on_a_cpu_only_box():
+    """The driver's build check: __graft_entry__.build() compiles (or finds up to date) the in-tree library, loads it and
+    checks the ABI version - without a GPU."""
+    import importlib
+
+    g = importlib.import_module("__graft_entry__")
+    g.build()

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <initializer_list>
 #include <new>
 #include <vector>
 
@@ -67,6 +68,8 @@ struct ds_handle {
   int homo_type = -1;                 // the one type every slot flies, -1: mixed
   int32_t* d_env_t0 = nullptr;        // [n_envs] step counter at each env's last masked reset (ds_reset_envs), lazily allocated
   int32_t* d_roll_wp[2] = {nullptr, nullptr};  // ds_rollout_host_table: double-buffered waypoint indices
+  const void* ok_ptrs[8] = {};        // target pointers already checked to be device-accessible (set_targets)
+  int ok_next = 0;
 };
 
 // Every entry point runs on the handle's device and puts the caller's current device back on exit: a process that
@@ -475,8 +478,33 @@ static void base_args(const ds_handle* h, DsArgs& a) {
   a.step_end = (int)(h->step_counter + h->cfg.substeps);
 }
 
-static int set_targets(DsArgs& a, const ds_targets* t) {
+// true if p is NULL or memory a kernel on the handle's device can write (device / managed / registered host)
+static bool device_writable(const ds_handle* h, const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type == cudaMemoryTypeDevice) return at.device == h->cfg.device;
+  return at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeHost;
+}
+
+// Target arrays are read by the kernels: they must be device-accessible memory.  cudaPointerGetAttributes costs about a
+// microsecond, which matters at the launch-bound sizes, so a pointer is looked up once and remembered (the callers pass the
+// same buffers step after step).
+static bool target_pointer_ok(ds_handle* h, const void* p) {
+  if (!p) return true;
+  for (const void* q : h->ok_ptrs)
+    if (q == p) return true;
+  if (!device_writable(h, p)) return false;
+  h->ok_ptrs[h->ok_next] = p;
+  h->ok_next = (h->ok_next + 1) % 8;
+  return true;
+}
+
+static int set_targets(ds_handle* h, DsArgs& a, const ds_targets* t) {
   if (!t) return DS_ERR_INVALID;
+  for (const void* p : {(const void*)t->pos_yaw, (const void*)t->vel, (const void*)t->acc, (const void*)t->table,
+                        (const void*)t->offset, (const void*)t->wp})
+    if (!target_pointer_ok(h, p)) return DS_ERR_INVALID;
   // rows are float4 / staged by 16-byte bulk copies: every array must be 16-byte aligned
   const void* ptrs[] = {t->pos_yaw, t->vel, t->acc, t->table, t->offset};
   for (const void* p : ptrs)
@@ -534,7 +562,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   ON_DEVICE(h);
   DsArgs a;
   base_args(h, a);
-  int rc = set_targets(a, tgt);
+  int rc = set_targets(h, a, tgt);
   if (rc != DS_OK) return rc;
   if (a.tmode == 3 && h->any_6dof) return DS_ERR_UNSUPPORTED;  // _INDIRateControl exists for the quad law only
   a.order = order;
@@ -598,15 +626,6 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   return DS_OK;
 }
 
-// true if p is NULL or memory a kernel on the handle's device can write (device / managed / registered host)
-static bool device_writable(const ds_handle* h, const void* p) {
-  if (!p) return true;
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  if (at.type == cudaMemoryTypeDevice) return at.device == h->cfg.device;
-  return at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeHost;
-}
-
 extern "C" int ds_set_env_outputs(ds_handle* h, uint8_t* done_env, float* reward_env) {
   if (!h) return DS_ERR_INVALID;
   ON_DEVICE(h);
@@ -647,7 +666,7 @@ static int control_common(ds_handle* h, const float* state, const ds_targets* tg
   DsArgs a;
   base_args(h, a);
   if (!rate_thrust) {
-    int rc = set_targets(a, tgt);
+    int rc = set_targets(h, a, tgt);
     if (rc != DS_OK) return rc;
     if (a.tmode == 3) {  // rate / thrust targets (RPYTAviary) on the resident or the caller's state
       if (h->any_6dof) return DS_ERR_UNSUPPORTED;

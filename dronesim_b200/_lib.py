@@ -88,6 +88,7 @@ SYMBOLS = {
     "ds_set_types": (C.c_int, [_H, C.POINTER(ds_type_params), C.c_int32, C.POINTER(C.c_uint8)]),
     "ds_reset": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ds_reset_envs": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ds_set_step_counter": (C.c_int, [_H, C.c_int64]),
     "ds_step": (C.c_int, [_H, C.POINTER(ds_targets), C.c_int32, C.c_int32, C.c_void_p]),
     "ds_physics_step": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ds_control_step": (C.c_int, [_H, C.POINTER(ds_targets), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -370,6 +370,36 @@ class SwarmCore:
             "cmd0123": c0, "cmd45": c1, "step_counter": int(v.step_counter),
         }
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    _STATE_KEYS = ("pos_thrust", "quat", "vel_rpm", "omega_wp", "lastvel_done", "lastrates_err", "cmd0123", "cmd45",
+                   "rpm0123", "rpm45", "ang_acc_filt")
+
+    def _raw_views(self):
+        v = L.ds_state_views()
+        L.check(L.lib().ds_views(self._h, C.byref(v)), self._h)
+        npad = int(v.n_pad)
+        out = {}
+        for k in self._STATE_KEYS:
+            ptr = getattr(v, k)
+            if ptr:
+                cols = 2 if k in ("cmd45", "rpm45") else 4
+                out[k] = torch.as_tensor(_CudaView(ptr, (npad, cols), "<f4", self), device=self.device)
+        return out, int(v.step_counter)
+
+    def state_dict(self) -> dict:
+        """The resident structure-of-arrays state (raw float32 words, integer fields included) + the step counter, on the
+        host: everything a rollout needs to continue bit-exactly in another handle of the same configuration."""
+        torch.cuda.current_stream(self.device).synchronize()
+        raw, sc = self._raw_views()
+        return {"step_counter": sc, **{k: t.cpu().clone() for k, t in raw.items()}}
+
+    def load_state_dict(self, sd: dict):
+        """Restore a ``state_dict`` into this handle (after ``reset``, which sizes everything)."""
+        raw, _ = self._raw_views()
+        for k, t in raw.items():
+            t.copy_(sd[k].to(self.device))
+        L.check(L.lib().ds_set_step_counter(self._h, int(sd["step_counter"])), self._h)
+
     def cmd(self) -> torch.Tensor:
         v = self.views()
         return torch.cat([v["cmd0123"], v["cmd45"]], dim=1)

@@ -442,6 +442,15 @@ extern "C" int ds_reset_envs(ds_handle* h, const uint8_t* mask_env, const float*
   return DS_OK;
 }
 
+extern "C" int ds_set_step_counter(ds_handle* h, int64_t step_counter) {
+  if (!h || step_counter < 0) return DS_ERR_INVALID;
+  if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
+  h->step_counter = step_counter;
+  h->first_action_pending = false;  // a restored state continues a rollout: its next action is the resident command
+  h->act_valid = false;
+  return DS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 static void base_args(const ds_handle* h, DsArgs& a) {
   memset(&a, 0, sizeof(a));

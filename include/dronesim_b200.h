@@ -216,6 +216,11 @@ int ds_reset(ds_handle* h, const float* pos0, const float* rpy0, const float* ve
 int ds_reset_envs(ds_handle* h, const uint8_t* mask_env, const float* pos0, const float* rpy0, const float* vel0,
                   const float* action0, const int32_t* wp0, void* stream);
 
+/* Checkpoint / resume: the resident state is the arrays ds_views exposes (copy them out and back in with any device
+ * copy) plus the host-side step counter, which this call restores (BaseAviary.step_counter, BaseAviary.py:554; it also keys
+ * the noise stream and the time limit).  Also clears the "first action pending" flag of a fresh ds_reset. */
+int ds_set_step_counter(ds_handle* h, int64_t step_counter);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* n_control_steps x { K physics substeps with the held command ; one INDI evaluation } fused in
  * one kernel per control step: examples/fly_INDI.py:217-245 for all vehicles at once.  `order` picks the kernel

@@ -166,16 +166,16 @@ def build(verbose: bool = False, force: bool = False, extra_flags=(), out_path: 
 
 
 def source_hash() -> str:
-    """sha256 over everything the built kernels are a function of (CUDA sources, the C header, the nvcc flags).
-    ``profiles/roofline_inputs.json`` is stamped with it; ``bench.py`` refuses ncu-derived constants measured on other sources."""
+    """sha256 over everything the step kernel is a function of: the device-side sources it is compiled from and the nvcc
+    flags (not the host API in ds_api.cu / the small kernels in ds_aux_kernels.cuh).  ``profiles/roofline_inputs.json`` is
+    stamped with it; ``bench.py`` refuses ncu-derived constants that were measured on other kernel sources."""
     import hashlib
 
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(f.encode())
-            h.update(open(os.path.join(CSRC, f), "rb").read())
-    h.update(open(os.path.join(INCLUDE, "dronesim_b200.h"), "rb").read())
+    for f in ("ds_lanes.cuh", "ds_device.cuh", "ds_wls.cuh", "ds_control.cuh", "ds_physics.cuh", "ds_kernels.cuh",
+              "ds_step_inst.cuh", "ds_step_inst.cu"):
+        h.update(f.encode())
+        h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()[:16]
 

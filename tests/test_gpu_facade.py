@@ -314,3 +314,36 @@ def test_ground_plane_and_auto_reset():
     assert (z[[2, 4]] > 0.0).all() and (z[[2, 4]] <= 0.05 + 1e-6).all()    # restarted from 0.05 m, still falling from there
     assert (z[[0, 1, 3, 5]] < 0.95).all()                                 # never reset: 48 substeps of free fall from 1 m
     env.close()
+
+
+def test_swarm_controller_equals_the_per_drone_controllers():
+    """``SwarmINDIControl`` (one launch for a mixed drone list) returns what the reference-style per-drone controller
+    objects return, call for call, over a closed loop with the aviary."""
+    _need_gpu()
+    from dronesim_b200.control.INDIControl import INDIControl
+    from dronesim_b200.control.INDIControl_6DOF import INDIControl as INDIControl6
+    from dronesim_b200.control.SwarmControl import SwarmINDIControl
+    from dronesim_b200.envs.CtrlAviary import CtrlAviary, Physics
+
+    models = ["robobee", "hexa_6DOF", "tello"]
+    xyz = np.array([[0.0, 0.0, 1.0], [1.5, 0.0, 1.2], [3.0, 0.0, 1.4]])
+    tgt = xyz + np.array([0.2, -0.1, 0.1])
+    envs = [CtrlAviary(drone_model=models, num_drones=3, initial_xyzs=xyz, physics=Physics.PYB_GND_DRAG_DW, aggregate_phy_steps=4)
+            for _ in range(2)]
+    per = [INDIControl(drone_model="robobee"), INDIControl6(drone_model="hexa_6DOF"), INDIControl(drone_model="tello")]
+    swarm = SwarmINDIControl(models)
+    acts = [{"0": np.full(4, 0.4), "1": np.full(6, 0.45), "2": np.full(4, 0.4)} for _ in range(2)]
+    for e in envs:
+        e.reset()
+    for step in range(40):
+        obs_a, _, _, _ = envs[0].step(acts[0])
+        obs_b, _, _, _ = envs[1].step(acts[1])
+        for j in range(3):
+            acts[0][str(j)], _, _ = per[j].computeControlFromState(control_timestep=4 / 240, state=obs_a[str(j)]["state"],
+                                                                   target_pos=tgt[j], target_rpy=np.array([0, 0, 0.2]))
+        acts[1], pos_e, yaw_e = swarm.computeControlFromState(4 / 240, obs_b, tgt, target_rpy=np.array([0, 0, 0.2]))
+        for j in range(3):
+            np.testing.assert_array_equal(acts[1][str(j)], acts[0][str(j)])
+    np.testing.assert_array_equal(envs[0].pos, envs[1].pos)
+    for c in per + [swarm] + envs:
+        c.close()

@@ -297,7 +297,9 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
       d.gw[i][0] = make_float2(r.ax, r.ay);
       d.gw[i][1] = make_float2(r.az, r.gx);
       d.gw[i][2] = make_float2(r.gy, r.gz);
-      for (int j = 0; j < p.n_v; ++j) d.alloc[i * 6 + j] = (float)p.alloc[i][j];
+      for (int j = 0; j < p.n_v; ++j) reinterpret_cast<float*>(&d.alloc2[i / 2][j])[i & 1] = (float)p.alloc[i][j];
+      reinterpret_cast<float*>(&d.plo[i / 2])[i & 1] = r.pmin;
+      reinterpret_cast<float*>(&d.phi[i / 2])[i & 1] = r.pmax;
     }
     d.rpm0_sum = (float)rpm0;
     for (int k = 0; k < 3; ++k) d.lat[k] = (float)lat[k];

@@ -301,7 +301,9 @@ __global__ void ds_wls_kernel(const DsTypeDev* types, const DsWlsDev* wls, int t
   bool feasible = true;
   for (int k = 0; k < 6; ++k) nu[k] = v[6 * i + k];
   for (int k = 0; k < 6; ++k) {
-    const float* a = tp.alloc + k * 6;
+    const float2* a2 = tp.alloc2[k / 2];  // rows in pairs: row k is the .x (even k) / .y (odd k) half
+    float a[6];
+    for (int j = 0; j < 6; ++j) a[j] = (k & 1) ? a2[j].y : a2[j].x;
     du[k] = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3] + a[4] * nu[4] + a[5] * nu[5];
     float umin = tp.rotor[k].pmin - cmd[6 * i + k], umax = tp.rotor[k].pmax - cmd[6 * i + k];
     feasible = feasible && (du[k] < umax + (1.0f - DS_WLS_MARGIN)) && (du[k] > umin - (1.0f - DS_WLS_MARGIN));

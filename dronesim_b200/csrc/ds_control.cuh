@@ -26,20 +26,30 @@ struct CtrlTarget { float x, y, z, yaw, vx, vy, vz, ax, ay, az; };
 struct CtrlMem { float lvx, lvy, lvz, lrx, lry, lrz, lthrust; float cmd[6]; float afx, afy, afz; };
 struct CtrlOut { float pex, pey, pez, yaw_err; int wls_iter; int sat; };
 
+// cmd = clip(cmd + A nu) (INDIControl.py:459, 486-487), two rotors per packed instruction.  Rotors beyond n_u have zero
+// rows and zero limits: their command stays 0, so the loop needs no per-rotor guard.
+template <bool NU6, int NV>
+__device__ __forceinline__ void ds_allocate(const DsTypeDev& tp, const float* nu, CtrlMem& m, CtrlOut& o, const f2* du_in = nullptr) {
+  constexpr int NP = NU6 ? 3 : 2;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    f2 du;
+    if (du_in) {
+      du = du_in[p];
+    } else {
+      du = ld2(tp.alloc2[p][0]) * nu[0];
+#pragma unroll
+      for (int j = 1; j < NV; ++j) du = ds_fma(ld2(tp.alloc2[p][j]), nu[j], du);
+    }
+    const f2 c = f2_make(m.cmd[2 * p], m.cmd[2 * p + 1]) + du;
+    const f2 cc = ds_min(ds_max(c, ld2(tp.plo[p])), ld2(tp.phi[p]));
+    o.sat += (f2_lo(cc) != f2_lo(c)) + (f2_hi(cc) != f2_hi(c));
+    m.cmd[2 * p] = f2_lo(cc); m.cmd[2 * p + 1] = f2_hi(cc);
+  }
+}
 template <bool NU6>
 __device__ __forceinline__ void ds_allocate_quad(const DsTypeDev& tp, const float nu[4], CtrlMem& m, CtrlOut& o) {
-  constexpr int NU = NU6 ? 6 : 4;
-#pragma unroll
-  for (int i = 0; i < NU; ++i) {
-    if (i < tp.n_u) {
-      const float* a = tp.alloc + i * 6;
-      float du = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3];  // INDIControl.py:459
-      float c = m.cmd[i] + du;                                              // :486
-      float cc = ds_clampf(c, tp.rotor[i].pmin, tp.rotor[i].pmax);          // :487
-      o.sat += (cc != c);
-      m.cmd[i] = cc;
-    }
-  }
+  ds_allocate<NU6, 4>(tp, nu, m, o);
 }
 
 // rate loop shared by both laws: returns nu[0..2] and updates last_rates (INDIControl.py:428-453).
@@ -164,18 +174,21 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
       nu[4] = R.m01 * aex + R.m11 * aey + R.m21 * aez;
       nu[5] = R.m02 * aex + R.m12 * aey + R.m22 * aez;
       m.lthrust = thrust;  // :598
-      // ---- allocation: first WLS iteration in closed form, du = M nu
-      float du[6];
+      // ---- allocation: first WLS iteration in closed form, du = M nu (rotor pairs on packed instructions)
+      f2 du2[3];
       bool feasible = true;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const float* a = tp.alloc + i * 6;
-        du[i] = a[0] * nu[0] + a[1] * nu[1] + a[2] * nu[2] + a[3] * nu[3] + a[4] * nu[4] + a[5] * nu[5];
-        float umin = tp.rotor[i].pmin - m.cmd[i], umax = tp.rotor[i].pmax - m.cmd[i];
+      for (int p = 0; p < 3; ++p) {
+        f2 d = ld2(tp.alloc2[p][0]) * nu[0];
+#pragma unroll
+        for (int j = 1; j < 6; ++j) d = ds_fma(ld2(tp.alloc2[p][j]), nu[j], d);
+        du2[p] = d;
         // wls_alloc.py:264 decides u_opt >= umax + 1 or u_opt <= umin - 1 in FP64; the FP32 first iterate is trusted only
         // when it clears the thresholds by DS_WLS_MARGIN (>> its rounding error), anything closer goes to the FP64
         // active-set routine, whose own first pass repeats the reference's test exactly
-        feasible = feasible && (du[i] < umax + (1.0f - DS_WLS_MARGIN)) && (du[i] > umin - (1.0f - DS_WLS_MARGIN));
+        const f2 c = f2_make(m.cmd[2 * p], m.cmd[2 * p + 1]);
+        const f2 hi = (ld2(tp.phi[p]) + (1.0f - DS_WLS_MARGIN)) - c, lo = (ld2(tp.plo[p]) - (1.0f - DS_WLS_MARGIN)) - c;
+        feasible = feasible && (f2_lo(d) < f2_lo(hi)) && (f2_lo(d) > f2_lo(lo)) && (f2_hi(d) < f2_hi(hi)) && (f2_hi(d) > f2_hi(lo));
       }
       o.wls_iter = 1;
       if (DEFER) {
@@ -189,7 +202,7 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
             for (int i = 0; i < 6; ++i) dst[i] = nu[i];
           }
 #pragma unroll
-          for (int i = 0; i < 6; ++i) du[i] = 0.f;
+          for (int p = 0; p < 3; ++p) du2[p] = f2_make(0.f, 0.f);
         }
       } else if (!feasible) {  // rare: run the active-set iterations in FP64
         const DsWlsDev* P = wls_tab + type_id;
@@ -202,15 +215,10 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
         }
         int it = ds_wls_alloc(P, v, umin, umax, u);
         o.wls_iter = it;
-        for (int i = 0; i < 6; ++i) du[i] = (it > 0) ? (float)u[i] : 0.f;  // non-convergence: hold the command
+        for (int p = 0; p < 3; ++p)  // non-convergence: hold the command
+          du2[p] = (it > 0) ? f2_make((float)u[2 * p], (float)u[2 * p + 1]) : f2_make(0.f, 0.f);
       }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float c = m.cmd[i] + du[i];  // :630
-        float cc = ds_clampf(c, tp.rotor[i].pmin, tp.rotor[i].pmax);
-        o.sat += (cc != c);
-        m.cmd[i] = cc;
-      }
+      ds_allocate<true, 6>(tp, nu, m, o, du2);  // cmd = clip(cmd + du) (:630-631)
     }
   }
 }

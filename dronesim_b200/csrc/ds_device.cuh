@@ -22,7 +22,7 @@
 #define DS_DW_ROWS (DS_TILE + DS_TILE / 2)       // float4 rows of one downwash position snapshot: (DS_TILE / D) envs x (D + 1) padded rows, D >= 2
 #define DS_DW_BUF (2 * DS_TILE)                  // rows reserved per snapshot buffer: the symmetric D = 16 variant stores every row twice (DS_TILE / 16 envs x 32 rows)
 
-#define DS_TYPE_PAD 8
+#define DS_TYPE_PAD 24
 struct __align__(16) DsRotorDev {
   float ax, ay, az, scale;   // thrust axis (body)            | PWM2RPM_SCALE
   float mx, my, mz, cnst;    // torque / unit thrust about CoM = (r - rc) x a + spin (km/kf) t | PWM2RPM_CONST
@@ -57,7 +57,8 @@ struct __align__(16) DsTypeDev {
   float kp, kd;
   float att[3];
   float rate[3];
-  float alloc[36];           // [n_u][6]
+  float2 alloc2[3][6];       // allocation matrix, rows in pairs: alloc2[p][j] = (A[2p][j], A[2p+1][j]) - two commands per FFMA2
+  float2 plo[3], phi[3];     // (MIN_PWM, MAX_PWM) of rotor pairs; rotors beyond n_u: 0 (their command stays 0)
   int n_u;
   int law;
   float rpm0_sum;            // sum_i PWM2RPM_CONST_i  (rpm of the all-zero action, BaseAviary.py:659-662)

@@ -26,6 +26,9 @@ template <> struct Lanes<f2>    { static constexpr int N = 2; typedef m2 Mask; }
 // ---- pack / unpack ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ f2 f2_make(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void f2_split(f2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ float f2_lo(f2 p) { float a, b; f2_split(p, a, b); return a; }
+__device__ __forceinline__ float f2_hi(f2 p) { float a, b; f2_split(p, a, b); return b; }
+__device__ __forceinline__ f2 ld2(const float2& c) { return f2_make(c.x, c.y); }   // a float2 from memory as a register pair
 __device__ __forceinline__ f2 to2(f2 x) { return x; }
 __device__ __forceinline__ f2 to2(float x) { return f2_make(x, x); }
 

@@ -41,9 +41,6 @@ struct PhysState {
 
 #define DS_DW_PAD 1       // shared-memory position rows are padded to D + 1 float4: envs of a warp hit disjoint banks
 
-__device__ __forceinline__ float f2_lo(f2 p) { float a, b; f2_split(p, a, b); return a; }
-__device__ __forceinline__ float f2_hi(f2 p) { float a, b; f2_split(p, a, b); return b; }
-__device__ __forceinline__ f2 ld2(const float2& c) { return f2_make(c.x, c.y); }
 
 // Rotation matrix of a unit quaternion (btMatrix3x3::setRotation, s = 2) as column pairs + third row:
 // c0 = (m00, m10), c1 = (m01, m11), c2 = (m02, m12), r = (m20, m21, m22).  16 FMA-pipe instructions.

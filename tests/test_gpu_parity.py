@@ -626,6 +626,94 @@ def test_full_size_single_type_properties(name, E):
 
 
 # ------------------------------------------------------------------------------------------
+# BASELINE sizes against the ORACLE: envs are independent, so the vectorised oracle simulates a sample of the envs of the
+# full-size run (first / last env, tile and CTA-wave boundaries, random ones) and those envs of the GPU state are compared
+# ------------------------------------------------------------------------------------------
+def _sample_envs(E, n, seed, per_tile):
+    rng = np.random.default_rng(seed)
+    fixed = [0, 1, per_tile - 1, per_tile, 592 * per_tile - 1, 592 * per_tile, E // 2, E - per_tile, E - 2, E - 1]
+    pick = np.unique(np.concatenate([np.array([e for e in fixed if 0 <= e < E]), rng.integers(0, E, n)]))
+    return pick.astype(np.int64)
+
+
+def test_full_size_hetero_swarm_sampled_envs_vs_oracle():
+    """configs[3] at 65,536 envs x 16 drones: 1 s closed loop, 74 sampled envs against the vectorised FP64 oracle."""
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.vehicles import load_vehicle
+    from dronesim_b200.workloads import hetero16
+    from oracle.batch import BatchOracle
+
+    E, T = 65536, 30
+    models, K, flags, pos0, act0, tgt = hetero16(E, seed=3, dtype=np.float32)
+    vts = [load_vehicle(m) for m in models]
+    core = SwarmCore(vts, E, integrator="quat", aggregate_phy_steps=K, stats=True, **flags)
+    core.reset(pos0, action0=act0)
+    core.step(core.targets_per_vehicle(tgt), T)
+    torch.cuda.synchronize()
+    pick = _sample_envs(E, 64, 11, per_tile=8)  # 128 vehicles per tile = 8 envs
+    S = len(pick)
+    bo = BatchOracle(vts, S, gnd=flags["ground"], drag=flags["drag"], dw=flags["downwash"], aggregate_phy_steps=K)
+    p0 = pos0[pick].astype(np.float64)
+    bo.reset(p0)
+    tpos = tgt.reshape(E, 16, 4)[pick, :, :3].astype(np.float64)
+    act = act0[pick].astype(np.float64)
+    for _ in range(T):
+        bo.physics_step(act)
+        act = bo.control_step(tpos)
+    v = core.views()
+    rows = (pick[:, None] * 16 + np.arange(16)[None, :]).reshape(-1)
+    gp = v["pos"].cpu().numpy()[rows]
+    gq = v["quat"].cpu().numpy()[rows]
+    gv = v["vel"].cpu().numpy()[rows]
+    assert np.abs(gp - bo.pos.reshape(-1, 3)).max() <= POS_TOL
+    assert angle_between(gq, bo.quat.reshape(-1, 4)).max() <= ATT_TOL
+    assert np.abs(gv - bo.vel.reshape(-1, 3)).max() <= 2e-3
+    st = core.stats()
+    assert st["non_finite"] == 0 and st["control_evals"] == E * 16 * T
+    core.close()
+
+
+@pytest.mark.parametrize("name,E,T", [("traj_quad", 4096, 96), ("hexa_circle", 65536, 96)])
+def test_full_size_single_type_sampled_envs_vs_oracle(name, E, T):
+    """configs[1] / configs[2] at their BASELINE env counts, 1 s at 96 Hz control, sampled envs against the oracle."""
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.vehicles import load_vehicle
+    from dronesim_b200.workloads import single_type
+    from oracle.batch import BatchOracle
+
+    models, K, flags, pos0, act0, tab, wp0 = single_type(name, E, seed=5)
+    vts = [load_vehicle(m) for m in models]
+    core = SwarmCore(vts, E, integrator="quat", aggregate_phy_steps=K, stats=True, **flags)
+    core.reset(pos0, action0=act0, wp0=wp0)
+    core.step(core.targets_table(tab), T)
+    torch.cuda.synchronize()
+    pick = _sample_envs(E, 96, 13, per_tile=128)
+    S = len(pick)
+    bo = BatchOracle(vts, S, gnd=flags["ground"], drag=flags["drag"], dw=flags["downwash"], aggregate_phy_steps=K)
+    bo.reset(pos0[pick])
+    wp = wp0[pick].astype(np.int64)
+    act = act0[pick].copy()
+    for _ in range(T):
+        bo.physics_step(act)
+        act = bo.control_step(tab[wp, 0:3].reshape(S, 1, 3), tvel=tab[wp, 3:6].reshape(S, 1, 3),
+                              tacc=tab[wp, 6:9].reshape(S, 1, 3), tyaw=tab[wp, 9].reshape(S, 1))
+        wp = np.where(wp < tab.shape[0] - 1, wp + 1, 0)
+    v = core.views()
+    gp = v["pos"].cpu().numpy()[pick]
+    gq = v["quat"].cpu().numpy()[pick]
+    assert np.abs(gp - bo.pos.reshape(-1, 3)).max() <= POS_TOL, name
+    assert angle_between(gq, bo.quat.reshape(-1, 4)).max() <= ATT_TOL, name
+    np.testing.assert_array_equal(v["wp_counter"].cpu().numpy()[pick], wp)
+    cmd = np.concatenate([v["cmd0123"].cpu().numpy(), v["cmd45"].cpu().numpy()], axis=1)[pick]
+    nu = 6 if "hexa" in models[0] else 4
+    np.testing.assert_allclose(cmd[:, :nu], act.reshape(S, 6)[:, :nu], atol=1e-4)
+    assert core.stats()["non_finite"] == 0
+    core.close()
+
+
+# ------------------------------------------------------------------------------------------
 # rotor noise (BaseAviary.py:1429-1432, 1518-1543) from the counter-based source: same stream in the oracle, so the
 # noisy closed loop is compared trajectory-for-trajectory; reproducible; independent of the sharding
 # ------------------------------------------------------------------------------------------

@@ -8,16 +8,27 @@
 #error "compile ds_step_inst.cu with -DDS_INST_INTEG=0|1 -DDS_INST_MODE=0|1|2 -DDS_INST_NU6=0|1"
 #endif
 
-// two tile stages of dynamic shared memory (> 48 KB: opt in once per instantiation and device)
+// two tile stages of dynamic shared memory (> 48 KB: opt in once per instantiation and device).  `grid` arrives as the
+// DS_MIN_CTAS-per-SM cap; variants whose registers and shared memory let more CTAs share an SM (the single-vehicle-env
+// variants: ~80 registers, no downwash snapshot, no type table in shared memory -> 5 CTAs) get a grid to match, so that a
+// fifth tile per SM is in flight on the HBM-bound K = 2 workloads.
 template <class ARGS, void (*KERNEL)(const ARGS)>
-static void launch5(const ARGS& args, int grid, cudaStream_t st) {
+static void launch5(const ARGS& args, int n_tiles, int grid, cudaStream_t st) {
   constexpr int kSmem = 2 * ds_stage_bytes<DS_INST_MODE>();
-  static bool opted[64] = {};
+  static int occ[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !opted[dev]) {
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!occ[dev]) {
     cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    opted[dev] = true;
+    cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, KERNEL, DS_TILE, kSmem) != cudaSuccess || n < DS_MIN_CTAS) n = DS_MIN_CTAS;
+    occ[dev] = n;
+  }
+  if (occ[dev] > DS_MIN_CTAS && grid < n_tiles) {
+    grid = grid / DS_MIN_CTAS * occ[dev];
+    if (grid > n_tiles) grid = n_tiles;
   }
   KERNEL<<<grid, DS_TILE, kSmem, st>>>(args);
 }
@@ -31,11 +42,11 @@ static void launch4b(const DsArgs& a, const DsTypeDev* homo, int grid, cudaStrea
     DsArgsH ah;
     ah.a = a;
     ah.tp = *homo;
-    launch5<DsArgsH, ds_step_kernel<DS_INST_INTEG, DW, NU6, WS, DS_INST_MODE, FX, false, true, RC>>(ah, grid, st);
+    launch5<DsArgsH, ds_step_kernel<DS_INST_INTEG, DW, NU6, WS, DS_INST_MODE, FX, false, true, RC>>(ah, a.n_tiles, grid, st);
     return;
   }
 #endif
-  launch5<DsArgs, ds_step_kernel<DS_INST_INTEG, DW, NU6, WS, DS_INST_MODE, FX, EXT, false, RC>>(a, grid, st);
+  launch5<DsArgs, ds_step_kernel<DS_INST_INTEG, DW, NU6, WS, DS_INST_MODE, FX, EXT, false, RC>>(a, a.n_tiles, grid, st);
 }
 
 // RC: some type has a centre-of-mass offset (quaternion integrator only; the extension variants always carry it)
@@ -65,8 +76,15 @@ static void launch2(bool warpsync, const DsArgs& a, const DsTypeDev* homo, int g
   if (a.ext) { launch3<DW, NU6, -1, true>(warpsync, a, homo, grid, st); return; }
 #endif
   // (the ground plane is a run-time flag as well: it rides in the FX = -1 variants only)
-  if (DW != 0 && (a.flags & 3u) == 3u && !(a.flags & 64u)) launch3<DW, NU6, 3, false>(warpsync, a, homo, grid, st);
-  else launch3<DW, NU6, -1, false>(warpsync, a, homo, grid, st);
+  if (DW != 0 && (a.flags & 3u) == 3u && !(a.flags & 64u)) { launch3<DW, NU6, 3, false>(warpsync, a, homo, grid, st); return; }
+#if DS_INST_INTEG == 0
+  // single-vehicle envs (BASELINE configs[1] / [2]): no add-ons, or ground effect + drag, at compile time too
+  if (DW == 0 && !(a.flags & 64u)) {
+    if ((a.flags & 3u) == 0u) { launch3<0, NU6, 0, false>(warpsync, a, homo, grid, st); return; }
+    if ((a.flags & 3u) == 3u) { launch3<0, NU6, 3, false>(warpsync, a, homo, grid, st); return; }
+  }
+#endif
+  launch3<DW, NU6, -1, false>(warpsync, a, homo, grid, st);
 }
 
 #define DS_CONCAT3_(a, b, c) a##b##_##c

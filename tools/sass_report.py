@@ -37,8 +37,8 @@ print()
 print("# the step-kernel instantiations the bench launches: hetero16 (mixed types, symmetric downwash, compile-time ground + drag, CoM")
 print("# offsets), quad_k8 / traj_quad (homogeneous quads), hexa_circle (homogeneous hexas, CoM offsets)")
 names = subprocess.run(["c++filt"], input="\n".join(perk.keys()), capture_output=True, text=True).stdout.splitlines()
-want = ("<0, 2, true, true, 0, 3, false, false, true>", "<0, 0, false, true, 0, -1, false, true, false>",
-        "<0, 0, true, true, 0, -1, false, true, true>")
+want = ("<0, 2, true, true, 0, 3, false, false, true>", "<0, 0, false, true, 0, 0, false, true, false>",
+        "<0, 0, true, true, 0, 3, false, true, true>")
 for k, n in zip(perk.keys(), names):
     if "ds_step_kernel" in n and any(t in n for t in want):
         c = perk[k]

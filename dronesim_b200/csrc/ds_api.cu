@@ -38,7 +38,7 @@ struct ds_handle {
   int* d_wls_count = nullptr;   // [2]: queue length, exit counter of the fix-up kernel (which re-arms both)
   int* d_wls_index = nullptr;   // [n]
   float* d_wls_nu = nullptr;    // [n][6]
-  int* d_tile_counter = nullptr;  // [2]: ticket counter, exit counter of the step kernel (whose last CTA re-arms both)
+  int* d_tile_counter = nullptr;  // ticket counter of the step kernel (re-armed by the holder of a launch's last ticket)
   uint8_t* env_done_out = nullptr;  // ds_set_env_outputs
   float* env_reward_out = nullptr;
   float* d_cmd_scratch = nullptr;  // [n][6]: un-fused control -> physics hand-over (order 1 with 6-DOF types)
@@ -546,7 +546,6 @@ static int set_targets(ds_handle* h, DsArgs& a, const ds_targets* t) {
 // translation units build in parallel; see ds_step_inst.cuh for the dispatcher.
 static void launch_step(int mode, ds_handle* h, DsArgs& a, cudaStream_t st) {
   a.tile_counter = h->d_tile_counter;
-  a.tile_done = h->d_tile_counter + 1;
   // downwash variant: 0 off, 1 every ordered pair, 2 symmetric pairs (16 drones per env, one Gaussian width for all types)
   int dw = ((a.flags & DS_FLAG_DOWNWASH) != 0 && a.D > 1) ? 1 : 0;
   if (dw && a.D == 16 && h->dw_uniform && !(h->cfg.flags & DS_FLAG_DW_ORDERED_PAIRS)) dw = 2;

@@ -46,27 +46,46 @@ __device__ __forceinline__ float ds_warp_min(float v) {
 // registers across the persistent tile loop; one warp-shuffle reduction + atomics per CTA at the end.
 enum { ST_NCTRL = 0, ST_ERR2, ST_SAT, ST_WLS_SLOW, ST_WLS_FAIL, ST_NONFINITE, ST_MINZ, ST_DONE, ST_COUNT };
 
-__device__ __forceinline__ void ds_flush_stats(const float* sh_stat, double* stats) {
+// One reduction per CTA (warp shuffles, then the four warp leaders through shared memory), then fire-and-forget
+// reductions (RED, no return value to wait for) on the global accumulators: nothing at the end of a CTA waits for
+// global memory.  Min altitude without a compare-and-swap loop: non-negative doubles order like their bit patterns
+// taken as signed integers, negative ones in reverse, and every negative pattern is below every non-negative one as a
+// signed integer but above it as an unsigned one - so a non-negative candidate is a signed min, a negative one an
+// unsigned max, and either is correct against whatever the slot holds.
+__device__ __forceinline__ void ds_flush_stats(float* sh_stat, double* stats) {
   const int t = threadIdx.x;
   float v[ST_COUNT];
 #pragma unroll
   for (int i = 0; i < ST_COUNT; ++i) v[i] = sh_stat[i * DS_TILE + t];
 #pragma unroll
   for (int i = 0; i < ST_COUNT; ++i) v[i] = (i == ST_MINZ) ? ds_warp_min(v[i]) : ds_warp_sum(v[i]);
+  __syncthreads();  // every thread has read its column
   if ((t & 31) == 0) {
 #pragma unroll
-    for (int i = 0; i < ST_COUNT; ++i)
-      if (i != ST_MINZ && v[i] != 0.f) atomicAdd(stats + i, (double)v[i]);
-    // min altitude: doubles order like their bit patterns for non-negative values only, so use a CAS loop
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(stats + ST_MINZ);
-    unsigned long long old = *p;
-    while (__longlong_as_double((long long)old) > (double)v[ST_MINZ]) {
-      unsigned long long assumed = old;
-      old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong((double)v[ST_MINZ]));
-      if (old == assumed) break;
+    for (int i = 0; i < ST_COUNT; ++i) sh_stat[i * (DS_TILE / 32) + (t >> 5)] = v[i];
+  }
+  __syncthreads();
+  if (t < ST_COUNT) {
+    float r = sh_stat[t * (DS_TILE / 32)];
+#pragma unroll
+    for (int w = 1; w < DS_TILE / 32; ++w) {
+      const float x = sh_stat[t * (DS_TILE / 32) + w];
+      r = (t == ST_MINZ) ? fminf(r, x) : r + x;
+    }
+    if (t != ST_MINZ) {
+      if (r != 0.f) atomicAdd(stats + t, (double)r);
+    } else {
+      const double d = (double)r + 0.0;  // -0.0 -> +0.0
+      if (d >= 0.0) atomicMin(reinterpret_cast<long long*>(stats + t), __double_as_longlong(d));
+      else atomicMax(reinterpret_cast<unsigned long long*>(stats + t), (unsigned long long)__double_as_longlong(d));
     }
   }
 }
+
+// Out-of-line copy for the kernels with a long substep loop: inlined, the epilogue changes the register allocation of
+// the whole kernel (measured on the 16-drone mixed swarm: +0.8 % per step); the short single-vehicle-env kernels keep it inline
+// (the call costs them 0.7 %).
+static __device__ __noinline__ void ds_flush_stats_call(float* sh_stat, double* stats) { ds_flush_stats(sh_stat, stats); }
 
 // ---------------------------------------------------------------------------------------------
 // Tile staging: bulk asynchronous copies (TMA unit, cp.async.bulk) global -> shared, two stages per CTA.
@@ -329,6 +348,16 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __g
       }
     }
 
+    // table targets: the row this vehicle's control law will read after the K substeps is requested into L1 now (its
+    // index sits in the staged tile), so that the gather's latency hides behind the physics - the K = 2 table workloads
+    // spent 16 % of their stall samples waiting for it.  Single-vehicle envs only: in the downwash kernels the K substeps are
+    // long enough to make the gather irrelevant, and the extra branch cost the 16-drone swarm 1 % (code generation).
+    if (MODE == 0 && DW == 0 && a.tmode == 1 && !a.t_wp) {
+      const float4* row = a.t_table + 3 * min(max(wp, 0), a.num_wp - 1);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 2));
+    }
+
     float rpm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // actual rotor speeds (motor model, EXT only)
     if (EXT) {
       const float4 R0 = a.s_r0[vv];
@@ -412,18 +441,15 @@ __global__ void __launch_bounds__(DS_TILE, DS_MIN_CTAS) ds_step_kernel(const __g
     if (tid == 0) {
       const int next_tile = 2 * (int)gridDim.x + ticket;
       const bool more = next_tile < a.n_tiles;
+      // every processed tile draws exactly one ticket and grid <= n_tiles, so a launch draws n_tiles tickets: whoever holds
+      // the last one re-arms the counter for the next launch (nobody draws after it), with no end-of-kernel handshake
+      if (ticket == a.n_tiles - 1) *a.tile_counter = 0;
       sh_tile[iter & 1] = more ? next_tile : -1;  // read two iterations (two barriers) from now
       if (more) ds_stage_issue<NU6, MODE>(a, next_tile, ds_stage_mem + (iter & 1) * STAGE, &sh_bar[iter & 1]);
     }
   }
-  if (stats_on) ds_flush_stats(sh_stat, a.stats);
-  // the last CTA out re-arms the ticket counter for the next launch (every CTA has drawn its last ticket by now)
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(a.tile_done, 1) == (int)gridDim.x - 1) {
-      *a.tile_counter = 0;
-      *a.tile_done = 0;
-    }
+  if (stats_on) {
+    if (DW == 0) ds_flush_stats(sh_stat, a.stats);
+    else ds_flush_stats_call(sh_stat, a.stats);
   }
 }
-

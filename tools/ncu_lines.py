@@ -1,9 +1,10 @@
 """Aggregate an ncu source-page export (cuda,sass) into executed instructions per CUDA source line.
-Usage: python tools/ncu_lines.py <report.ncu-rep> [top_n]"""
+Usage: python tools/ncu_lines.py <report.ncu-rep> [top_n] [samples]"""
 import collections, csv, subprocess, sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+by_samples = len(sys.argv) > 3 and sys.argv[3] == "samples"  # sort by stall samples instead of executed instructions
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur, nk = None, 0
@@ -34,5 +35,5 @@ for (f, l), v in agg.items():
     byfile[f] += v[0]
 print("total warp instructions (all captured launches):", tot)
 print({k: "%.1f%%" % (100 * v / tot) for k, v in byfile.items() if v})
-for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     print("%-16s %4d inst %5.2f%% samples %5.2f%%  %s" % (f, l, 100 * v[0] / tot, 100 * v[1] / stot, v[2]))

@@ -4,11 +4,11 @@ set -u
 TAG=${1:-r2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-for G in 1 2 4 8; do
+for G in ${H2D_RANKS-1 2 4 8}; do   # H2D_RANKS="" skips the bandwidth micro-benchmark
   $TR --nproc-per-node $G --master-port $((29500+G)) tools/ubench/h2d_concurrent.py 2>/dev/null | grep ranks | tee -a gpurun_out/h2d_concurrent_${TAG}.txt
 done
 nvidia-smi topo -m > gpurun_out/topo_${TAG}.txt 2>&1; lscpu | grep -E "Model name|Socket|NUMA|^CPU\(s\)" >> gpurun_out/topo_${TAG}.txt
-for G in 8 4 2; do
+for G in ${BENCH_RANKS-8 4 2}; do
   $TR --nproc-per-node $G --master-port $((29600+G)) bench.py --gpus $G --steps 100 --warmup 10 --no-others > gpurun_out/bench_${G}gpu_${TAG}.json 2> gpurun_out/bench_${G}gpu_${TAG}.err
   echo "bench $G GPUs rc=$?"
   python - <<PY

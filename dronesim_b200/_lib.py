@@ -25,6 +25,7 @@ DS_NUM_STATS = 16
 DS_OK, DS_ERR_INVALID, DS_ERR_CUDA, DS_ERR_STATE, DS_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 DS_INTEG_QUAT, DS_INTEG_RPY = 0, 1
 DS_FLAG_GROUND, DS_FLAG_DRAG, DS_FLAG_DOWNWASH, DS_FLAG_STATS, DS_FLAG_DW_ORDERED_PAIRS, DS_FLAG_TYPES_IN_SMEM, DS_FLAG_GROUND_PLANE = 1, 2, 4, 8, 16, 32, 64
+DS_FLAG_DEBUG_REDZONES = 128
 DS_LAW_QUAD, DS_LAW_6DOF = 0, 1
 DS_DONE_GOAL, DS_DONE_FLOOR, DS_DONE_TIME = 1, 2, 4
 DS_ORDER_PHYSICS_THEN_CONTROL, DS_ORDER_CONTROL_THEN_PHYSICS = 0, 1
@@ -107,6 +108,7 @@ SYMBOLS = {
     "ds_rollout_host_table": (C.c_int, [_H, C.POINTER(ds_targets), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ds_debug_wls": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                C.c_int32, C.c_void_p]),
+    "ds_debug_check_redzones": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "ds_debug_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "ds_strerror": (C.c_char_p, [C.c_int]),
     "ds_last_cuda_error": (C.c_int, [_H]),

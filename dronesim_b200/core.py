@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -93,7 +94,7 @@ class SwarmCore:
                  freq: float = 240.0, aggregate_phy_steps: int = 1, neighbourhood_radius: float = math.inf,
                  gravity: float = 9.8, goal=None, goal_radius: float = 0.3, z_min=None, max_steps: int = 0,
                  device: int = 0, env_offset: int = 0, assets_dir: Optional[str] = None, dw_ordered_pairs: bool = False,
-                 types_in_smem: bool = False, ground_plane_z: Optional[float] = None,
+                 types_in_smem: bool = False, ground_plane_z: Optional[float] = None, debug_redzones: bool = False,
                  motor_tau: float = 0.0, acc_filter_hz: float = 0.0, reward_mode: int = 0,
                  noise_force_sigma: float = 0.0, noise_torque_sigma: float = 0.0, noise_seed: int = 0):
         lib = L.lib()
@@ -109,6 +110,9 @@ class SwarmCore:
         self.composite = composite
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)
+        # guard bands around every device buffer of the handle (check_redzones(); close() raises if one was overwritten);
+        # DRONESIM_B200_REDZONES=1 turns them on for every core of the process (how the GPU test-suite is run once per change)
+        self._redzones = bool(debug_redzones) or os.environ.get("DRONESIM_B200_REDZONES") == "1"
         cfg = L.ds_config()
         cfg.n_envs, cfg.drones_per_env, cfg.substeps = self.E, self.D, self.K
         cfg.integrator = L.DS_INTEG_RPY if integrator == "rpy" else L.DS_INTEG_QUAT
@@ -116,7 +120,8 @@ class SwarmCore:
                      | (L.DS_FLAG_DOWNWASH if downwash else 0) | (L.DS_FLAG_STATS if stats else 0)
                      | (L.DS_FLAG_DW_ORDERED_PAIRS if dw_ordered_pairs else 0)
                      | (L.DS_FLAG_TYPES_IN_SMEM if types_in_smem else 0)
-                     | (L.DS_FLAG_GROUND_PLANE if ground_plane_z is not None else 0))
+                     | (L.DS_FLAG_GROUND_PLANE if ground_plane_z is not None else 0)
+                     | (L.DS_FLAG_DEBUG_REDZONES if self._redzones else 0))
         cfg.ground_plane_z = float(ground_plane_z) if ground_plane_z is not None else 0.0
         cfg.device, cfg.sim_freq, cfg.gravity = self.device_index, float(freq), float(gravity)
         cfg.neighbourhood_radius = float(neighbourhood_radius)
@@ -152,11 +157,21 @@ class SwarmCore:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def check_redzones(self) -> int:
+        """Guard-band bytes around the handle's device buffers that a kernel has overwritten (cores created with
+        ``debug_redzones=True`` / DRONESIM_B200_REDZONES=1; synchronises the device)."""
+        bad = C.c_int64(0)
+        L.check(L.lib().ds_debug_check_redzones(self._h, C.byref(bad)), self._h)
+        return int(bad.value)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            bad = self.check_redzones() if getattr(self, "_redzones", False) else 0
             L.lib().ds_destroy(self._h)
             self._h = C.c_void_p()
             self._views = None
+            if bad:
+                raise RuntimeError("dronesim_b200: %d guard-band bytes around the core's device buffers were overwritten" % bad)
 
     def __del__(self):
         try:

@@ -70,7 +70,38 @@ struct ds_handle {
   int32_t* d_roll_wp[2] = {nullptr, nullptr};  // ds_rollout_host_table: double-buffered waypoint indices
   const void* ok_ptrs[8] = {};        // target pointers already checked to be device-accessible (set_targets)
   int ok_next = 0;
+  // DS_FLAG_DEBUG_REDZONES: every device buffer of the handle sits between two guard bands (ds_debug_check_redzones)
+  struct Zone { void* user; void* base; size_t bytes; };
+  std::vector<Zone> zones;
 };
+
+// Device allocations of a handle.  With DS_FLAG_DEBUG_REDZONES each buffer is preceded and followed by DS_REDZONE bytes of a
+// known pattern that no kernel may touch; ds_debug_check_redzones counts the bytes that changed.  (compute-sanitizer is not
+// available on every GPU pool; this is the library's own check for stray global stores, run by the GPU tests on ragged sizes.)
+static const size_t DS_REDZONE = 4096;
+static const int DS_REDZONE_BYTE = 0xA5;
+static cudaError_t h_malloc(ds_handle* h, void** p, size_t bytes) {
+  if (!(h->cfg.flags & DS_FLAG_DEBUG_REDZONES)) return cudaMalloc(p, bytes);
+  const size_t body = (bytes + 255) & ~(size_t)255;
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc((void**)&base, body + 2 * DS_REDZONE);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(base, DS_REDZONE_BYTE, body + 2 * DS_REDZONE);
+  if (e != cudaSuccess) { cudaFree(base); return e; }
+  *p = base + DS_REDZONE;
+  h->zones.push_back({*p, base, bytes});
+  return cudaSuccess;
+}
+static void h_free(ds_handle* h, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->zones.size(); ++i)
+    if (h->zones[i].user == p) {
+      cudaFree(h->zones[i].base);
+      h->zones.erase(h->zones.begin() + i);
+      return;
+    }
+  cudaFree(p);
+}
 
 // Every entry point runs on the handle's device and puts the caller's current device back on exit: a process that
 // drives several GPUs (or PyTorch's own current-device bookkeeping) must not see it change behind its back.
@@ -118,8 +149,7 @@ static void free_all(ds_handle* h) {
                   h->d_host_tgt, h->d_obs, h->d_done_env, h->d_roll_tgt[0], h->d_roll_tgt[1], h->d_roll_done[0],
                   h->d_roll_done[1], h->d_log_ids, h->d_log_states, h->s_r0, h->s_r1, h->s_af, h->d_wls_count, h->d_wls_index, h->d_wls_nu,
                   h->d_cmd_scratch, h->d_tile_counter, h->d_env_t0, h->d_roll_wp[0], h->d_roll_wp[1]};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  for (void* p : ptrs) h_free(h, p);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
     if (h->ev_computed[b]) cudaEventDestroy(h->ev_computed[b]);
@@ -159,7 +189,7 @@ extern "C" int ds_create(const ds_config* cfg, ds_handle** out) {
   const size_t np = (size_t)h->n_pad;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
-    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = h_malloc(h, p, bytes);
     if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
   };
   alloc((void**)&h->s_pos, np * 16); alloc((void**)&h->s_quat, np * 16); alloc((void**)&h->s_vel, np * 16);
@@ -320,14 +350,14 @@ extern "C" int ds_set_types(ds_handle* h, const ds_type_params* types, int32_t n
   }
   h->types_set = false;  // until the new table is resident (a CUDA failure below must not leave a half-updated handle usable)
   if (any_6dof && !h->d_wls_count) {  // deferred WLS slow path (ds_wls_fixup_kernel)
-    CK(cudaMalloc((void**)&h->d_wls_count, 2 * sizeof(int)));
+    CK(h_malloc(h, (void**)&h->d_wls_count, 2 * sizeof(int)));
     CK(cudaMemset(h->d_wls_count, 0, 2 * sizeof(int)));
-    CK(cudaMalloc((void**)&h->d_wls_index, (size_t)h->n * sizeof(int)));
-    CK(cudaMalloc((void**)&h->d_wls_nu, (size_t)h->n * 6 * sizeof(float)));
+    CK(h_malloc(h, (void**)&h->d_wls_index, (size_t)h->n * sizeof(int)));
+    CK(h_malloc(h, (void**)&h->d_wls_nu, (size_t)h->n * 6 * sizeof(float)));
   }
   if (need_ext && !h->ext) {
     const size_t np = (size_t)h->n_pad;
-    CK(cudaMalloc((void**)&h->s_r0, np * 16)); CK(cudaMalloc((void**)&h->s_r1, np * 8)); CK(cudaMalloc((void**)&h->s_af, np * 16));
+    CK(h_malloc(h, (void**)&h->s_r0, np * 16)); CK(h_malloc(h, (void**)&h->s_r1, np * 8)); CK(h_malloc(h, (void**)&h->s_af, np * 16));
     CK(cudaMemset(h->s_r0, 0, np * 16)); CK(cudaMemset(h->s_r1, 0, np * 8)); CK(cudaMemset(h->s_af, 0, np * 16));
     h->ext = true;
   }
@@ -355,10 +385,10 @@ static int grid_for(const ds_handle* h, int blocks_wanted, int per_sm) {
 
 static int ensure_stage(ds_handle* h, size_t bytes) {
   if (h->stage_bytes >= bytes) return DS_OK;
-  if (h->d_stage) cudaFree(h->d_stage);
+  if (h->d_stage) h_free(h, h->d_stage);
   h->d_stage = nullptr;
   h->stage_bytes = 0;
-  CK(cudaMalloc((void**)&h->d_stage, bytes));
+  CK(h_malloc(h, (void**)&h->d_stage, bytes));
   h->stage_bytes = bytes;
   return DS_OK;
 }
@@ -422,7 +452,7 @@ extern "C" int ds_reset_envs(ds_handle* h, const uint8_t* mask_env, const float*
   ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   if (!h->d_env_t0) {
-    CK(cudaMalloc((void**)&h->d_env_t0, sizeof(int32_t) * (size_t)h->cfg.n_envs));
+    CK(h_malloc(h, (void**)&h->d_env_t0, sizeof(int32_t) * (size_t)h->cfg.n_envs));
     CK(cudaMemsetAsync(h->d_env_t0, 0, sizeof(int32_t) * (size_t)h->cfg.n_envs, st));
   }
   DsResetArgs a;
@@ -592,7 +622,7 @@ extern "C" int ds_step(ds_handle* h, const ds_targets* tgt, int32_t n_control_st
   if (order == DS_ORDER_CONTROL_THEN_PHYSICS && h->any_6dof) {
     // The fused kernel defers the rare FP64 WLS iterations to a follow-up kernel, which is too late when the physics of
     // the SAME launch needs the command: run the control kernel (in-line slow path), then the physics with its output.
-    if (!h->d_cmd_scratch) CK(cudaMalloc((void**)&h->d_cmd_scratch, (size_t)h->n * 6 * sizeof(float)));
+    if (!h->d_cmd_scratch) CK(h_malloc(h, (void**)&h->d_cmd_scratch, (size_t)h->n * 6 * sizeof(float)));
     for (int i = 0; i < n_control_steps; ++i) {
       rc = ds_control_step(h, tgt, a.ctrl_dt, h->d_cmd_scratch, nullptr, nullptr, stream);
       if (rc != DS_OK) return rc;
@@ -750,13 +780,13 @@ extern "C" int ds_log_attach(ds_handle* h, const int32_t* vehicles, int32_t n_ve
   ON_DEVICE(h);
   for (int i = 0; i < n_vehicles; ++i)
     if (vehicles[i] < 0 || vehicles[i] >= h->n) return DS_ERR_INVALID;
-  if (h->d_log_ids) cudaFree(h->d_log_ids);
-  if (h->d_log_states) cudaFree(h->d_log_states);
+  if (h->d_log_ids) h_free(h, h->d_log_ids);
+  if (h->d_log_states) h_free(h, h->d_log_states);
   h->d_log_ids = nullptr; h->d_log_states = nullptr;
   h->log_n = 0; h->log_cap = 0; h->log_count = 0; h->log_time.clear();
   if (n_vehicles == 0) return DS_OK;
-  CK(cudaMalloc((void**)&h->d_log_ids, sizeof(int32_t) * n_vehicles));
-  CK(cudaMalloc((void**)&h->d_log_states, sizeof(float) * (size_t)n_vehicles * DS_OBS_STRIDE * capacity));
+  CK(h_malloc(h, (void**)&h->d_log_ids, sizeof(int32_t) * n_vehicles));
+  CK(h_malloc(h, (void**)&h->d_log_states, sizeof(float) * (size_t)n_vehicles * DS_OBS_STRIDE * capacity));
   CK(cudaMemcpy(h->d_log_ids, vehicles, sizeof(int32_t) * n_vehicles, cudaMemcpyHostToDevice));
   CK(cudaMemset(h->d_log_states, 0, sizeof(float) * (size_t)n_vehicles * DS_OBS_STRIDE * capacity));
   h->log_n = n_vehicles; h->log_cap = capacity;
@@ -826,9 +856,9 @@ extern "C" int ds_step_host(ds_handle* h, const float* host_pos_yaw, float* host
   ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)h->n;
-  if (!h->d_host_tgt) CK(cudaMalloc((void**)&h->d_host_tgt, (size_t)h->n_pad * 16));
-  if (host_obs && !h->d_obs) CK(cudaMalloc((void**)&h->d_obs, n * DS_OBS_STRIDE * sizeof(float)));
-  if (host_done_env && !h->d_done_env) CK(cudaMalloc((void**)&h->d_done_env, (size_t)h->cfg.n_envs));
+  if (!h->d_host_tgt) CK(h_malloc(h, (void**)&h->d_host_tgt, (size_t)h->n_pad * 16));
+  if (host_obs && !h->d_obs) CK(h_malloc(h, (void**)&h->d_obs, n * DS_OBS_STRIDE * sizeof(float)));
+  if (host_done_env && !h->d_done_env) CK(h_malloc(h, (void**)&h->d_done_env, (size_t)h->cfg.n_envs));
   CK(cudaMemcpyAsync(h->d_host_tgt, host_pos_yaw, n * 16, cudaMemcpyHostToDevice, st));
   ds_targets t;
   memset(&t, 0, sizeof(t));
@@ -869,15 +899,15 @@ static int rollout_common(ds_handle* h, const ds_targets* table_tgt, const void*
     CK(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
-      CK(cudaMalloc((void**)&h->d_roll_done[b], E));
+      CK(h_malloc(h, (void**)&h->d_roll_done[b], E));
       CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_computed[b], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_drained[b], cudaEventDisableTiming));
     }
   }
   for (int b = 0; b < 2; ++b) {
-    if (!table_tgt && !h->d_roll_tgt[b]) CK(cudaMalloc((void**)&h->d_roll_tgt[b], (size_t)h->n_pad * 16));
-    if (table_tgt && !h->d_roll_wp[b]) CK(cudaMalloc((void**)&h->d_roll_wp[b], (size_t)h->n_pad * sizeof(int32_t)));
+    if (!table_tgt && !h->d_roll_tgt[b]) CK(h_malloc(h, (void**)&h->d_roll_tgt[b], (size_t)h->n_pad * 16));
+    if (table_tgt && !h->d_roll_wp[b]) CK(h_malloc(h, (void**)&h->d_roll_wp[b], (size_t)h->n_pad * sizeof(int32_t)));
   }
   for (int i = 0; i < n_steps; ++i) {
     const int b = i & 1;
@@ -933,6 +963,29 @@ extern "C" int ds_rollout_host_table(ds_handle* h, const ds_targets* tgt, const 
   if (!h || !tgt || !host_wp || n_steps <= 0 || tgt->mode != 1 || !tgt->table || tgt->num_wp <= 0) return DS_ERR_INVALID;
   if (!h->types_set || !h->is_reset) return DS_ERR_STATE;
   return rollout_common(h, tgt, host_wp, (size_t)h->n * sizeof(int32_t), n_steps, host_done_env, stream);
+}
+
+extern "C" int ds_debug_check_redzones(ds_handle* h, int64_t* corrupted_bytes) {
+  if (!h || !corrupted_bytes) return DS_ERR_INVALID;
+  if (!(h->cfg.flags & DS_FLAG_DEBUG_REDZONES)) return DS_ERR_UNSUPPORTED;
+  ON_DEVICE(h);
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned char> buf;
+  int64_t bad = 0;
+  for (const ds_handle::Zone& z : h->zones) {
+    const char* base = (const char*)z.base;
+    const char* user = (const char*)z.user;
+    const size_t body = (z.bytes + 255) & ~(size_t)255;
+    const char* spans[2][2] = {{base, user}, {user + z.bytes, user + body + DS_REDZONE}};
+    for (auto& sp : spans) {
+      const size_t len = (size_t)(sp[1] - sp[0]);
+      buf.resize(len);
+      CK(cudaMemcpy(buf.data(), sp[0], len, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < len; ++i) bad += (buf[i] != (unsigned char)DS_REDZONE_BYTE);
+    }
+  }
+  *corrupted_bytes = bad;
+  return DS_OK;
 }
 
 extern "C" int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out,

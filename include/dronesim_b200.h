@@ -59,7 +59,10 @@ enum { DS_FLAG_GROUND = 1u, DS_FLAG_DRAG = 2u, DS_FLAG_DOWNWASH = 4u, DS_FLAG_ST
        DS_FLAG_TYPES_IN_SMEM = 32u,
        /* the ground plane of the reference's PyBullet world as a hard floor at ds_config.ground_plane_z (off by default:
         * the reference's explicit-dynamics formulas have no contact) */
-       DS_FLAG_GROUND_PLANE = 64u };
+       DS_FLAG_GROUND_PLANE = 64u,
+       /* diagnostics: every device buffer of the handle is allocated between two 4 KiB guard bands of a known pattern;
+        * ds_debug_check_redzones counts the guard bytes a kernel has overwritten (the library's own stray-store check) */
+       DS_FLAG_DEBUG_REDZONES = 128u };
 
 /* control laws: which reference controller class flies the type */
 enum { DS_LAW_QUAD = 0 /* INDIControl.py */, DS_LAW_6DOF = 1 /* INDIControl_6DOF.py */ };
@@ -304,6 +307,12 @@ int ds_rollout_host_table(ds_handle* h, const ds_targets* tgt, const int32_t* ho
  * force_slow != 0 skips the closed-form first iteration and always runs the FP64 active-set loop. */
 int ds_debug_wls(ds_handle* h, int32_t type_id, const float* v, const float* cmd, float* du_out, int32_t* iter_out,
                  int32_t* w_out, int32_t n, int32_t force_slow, void* stream);
+
+/* Handles created with DS_FLAG_DEBUG_REDZONES: synchronises the device and writes to *corrupted_bytes (HOST) how many
+ * guard-band bytes around the handle's device buffers no longer hold the fill pattern (0 = no kernel stored outside
+ * its buffers).  DS_ERR_UNSUPPORTED for handles created without the flag.  The reference has no counterpart (NumPy
+ * raises IndexError on a stray index, BaseAviary.py:718-732 slices); this replaces it for the CUDA core. */
+int ds_debug_check_redzones(ds_handle* h, int64_t* corrupted_bytes);
 
 /* FP32 issue-rate micro-benchmark (bench bookkeeping: the FP32 roofline denominator, which
  * MEASURED_PEAKS.json does not carry).  Runs 8 independent FFMA chains per thread on every SM of

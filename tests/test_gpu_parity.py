@@ -1332,3 +1332,87 @@ def test_checkpoint_resume_is_bit_exact():
     assert (va["done_bits"].cpu().numpy() & 4).all()  # the time limit (60 substeps) fired in both
     a.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------------------
+# stray-store check (compute-sanitizer is closed on the GPU pool): every device buffer of a core created with
+# debug_redzones=True sits between two guard bands; ragged sizes, every entry point, then the bands must be intact.
+# (DRONESIM_B200_REDZONES=1 python -m pytest tests -m gpu runs the whole suite this way: close() raises on corruption.)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("models,E,flags,ext", [
+    (["robobee"], 1, {}, {}),
+    (["robobee", "hexa_6DOF", "tello"], 43, dict(ground=True, drag=True, downwash=True), {}),  # 129 vehicles: ragged last tile
+    (["robobee", "tello"] * 4 + ["hexa_6DOF"] * 8, 9, dict(ground=True, drag=True, downwash=True), {}),  # symmetric-pair kernel
+    (["hexa_6DOF"], 131, dict(ground=True, drag=True), {}),  # homogeneous variant, compile-time add-ons
+    (["robobee", "hexa_6DOF"], 65, dict(drag=True), dict(motor_tau=0.02, acc_filter_hz=40.0, noise_force_sigma=0.01, noise_seed=3)),
+])
+def test_redzones_stay_intact(models, E, flags, ext):
+    _need_gpu()
+    from dronesim_b200.core import SwarmCore
+
+    D = len(models)
+    N = E * D
+    rng = np.random.default_rng(5)
+    core = SwarmCore(models, E, aggregate_phy_steps=3, stats=True, debug_redzones=True, max_steps=1000, **flags, **ext)
+    pos0 = np.zeros((E, D, 3))
+    pos0[..., 0] = np.arange(D)[None, :] * 0.7
+    pos0[..., 2] = 1.0 + 0.3 * np.arange(D)[None, :]
+    pos0 += rng.uniform(-0.02, 0.02, pos0.shape)
+    act0 = np.full((E, D, 6), 0.4)
+    core.reset(pos0, action0=act0)
+    core.set_env_outputs()
+    tg = np.concatenate([pos0.reshape(-1, 3), np.zeros((N, 1))], axis=1)
+    core.step(core.targets_per_vehicle(tg), 4)
+    tab = np.zeros((7, 10))
+    tab[:, 2] = 1.0
+    core.step(core.targets_table(tab), 3)
+    core.get_obs(reward=True)
+    core.physics_step(torch.full((N, 6), 0.4, device="cuda"))
+    core.control_step(core.targets_per_vehicle(tg), 3 / 240.0)
+    core.log_attach(list(range(0, N, max(1, N // 5))), 8)
+    core.step(core.targets_per_vehicle(tg), 5)
+    core.log_read()
+    mask = np.zeros(E, dtype=bool)
+    mask[::2] = True
+    core.reset_envs(mask, pos0, action0=act0)
+    core.step(core.targets_per_vehicle(tg), 2)
+    T = 3
+    hp = torch.from_numpy(np.broadcast_to(tg.astype(np.float32), (T, N, 4)).copy()).pin_memory()
+    hd = torch.zeros((T, E), dtype=torch.uint8).pin_memory()
+    core.rollout_host(hp, hd)
+    hw = torch.zeros((T, N), dtype=torch.int32).pin_memory()
+    core.rollout_host_table(core.targets_table(tab), hw, hd)
+    ho = torch.zeros((N, 22), dtype=torch.float32).pin_memory()
+    core.step_host(hp[0], ho, hd[0])
+    if not ext:
+        core.load_state_dict(core.state_dict())
+    assert core.stats()["non_finite"] == 0
+    assert core.check_redzones() == 0
+    core.close()
+
+
+def test_redzones_detect_a_stray_store():
+    _need_gpu()
+    from dronesim_b200 import _lib as L
+    from dronesim_b200.core import SwarmCore, _CudaView
+    import ctypes as C
+
+    core = SwarmCore(["robobee"], 5, debug_redzones=True)
+    core.reset(np.zeros((5, 1, 3)) + [0.0, 0.0, 1.0])
+    assert core.check_redzones() == 0
+    v = L.ds_state_views()
+    L.check(L.lib().ds_views(core._h, C.byref(v)), core._h)
+    # one float just past the (padded) position array, one just before the quaternion array
+    past = torch.as_tensor(_CudaView(int(v.pos_thrust) + int(v.n_pad) * 16, (1,), "<f4", core), device="cuda")
+    before = torch.as_tensor(_CudaView(int(v.quat) - 4, (1,), "<f4", core), device="cuda")
+    past.fill_(1.0)
+    before.fill_(2.0)
+    torch.cuda.synchronize()
+    assert 1 <= core.check_redzones() <= 8
+    with pytest.raises(RuntimeError, match="guard-band"):
+        core.close()
+    if os.environ.get("DRONESIM_B200_REDZONES") != "1":
+        plain = SwarmCore(["robobee"], 5)
+        with pytest.raises(RuntimeError):  # DS_ERR_UNSUPPORTED: the handle has no guard bands
+            plain.check_redzones()
+        plain.close()

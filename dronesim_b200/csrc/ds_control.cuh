@@ -93,7 +93,7 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
   float asz = (o.pez * tp.kp + t.vz - s.vz) * tp.kd;
   float cax = (s.vx - m.lvx) * inv_dt, cay = (s.vy - m.lvy) * inv_dt, caz = (s.vz - m.lvz) * inv_dt;
   m.lvx = s.vx; m.lvy = s.vy; m.lvz = s.vz;
-  const bool six = (tp.law == 1);
+  const bool six = NU6 && (tp.law == 1);  // (a 6-DOF type makes every kernel of the handle an NU6 one)
   float tax = six ? 0.f : t.ax, tay = six ? 0.f : t.ay, taz = six ? 0.f : t.az;  // 6DOF ignores target_acc (:410)
   float aex = ds_clampf(asx + tax - cax, -6.f, 6.f);
   float aey = ds_clampf(asy + tay - cay, -6.f, 6.f);
@@ -138,6 +138,9 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
   float thrust = m.lthrust + dT;  // INDIControl.py:347 / INDIControl_6DOF.py:491
   o.wls_iter = 0;
 
+  // rate set-points (attitude loop) and the translational virtual controls of the lane's law
+  float nu[6];
+  float rsp0, rsp1, rsp2;
   if (!six) {
     float dphi = -u1 * (1.0f / T);
     float dtheta = u0 * ds_rcp(T * cphi);
@@ -155,70 +158,74 @@ __device__ __forceinline__ void ds_indi_control(const DsTypeDev& tp, const DsWls
     float ey = w * tq.y + x * tq.z - y * tq.w - z * tq.x;
     float ez = w * tq.z - x * tq.y + y * tq.x - z * tq.w;
     if (ew < 0.f) { ex = -ex; ey = -ey; ez = -ez; }  // quat_wrap_shortest, in place (quirk Q1)
-    float nu[4];
-    ds_rate_loop<EXT>(tp, s, inv_dt, acc_b, tp.att[0] * ex, tp.att[1] * ey, tp.att[2] * ez, m, nu);
+    rsp0 = tp.att[0] * ex; rsp1 = tp.att[1] * ey; rsp2 = tp.att[2] * ez;
     nu[3] = dT;  // thrust - last_thrust (:454); dT avoids the FP32 cancellation of (lt + dT) - lt
-    m.lthrust = thrust;
+    nu[4] = nu[5] = 0.f;
+  } else {
+    o.yaw_err = 0.f - psi;  // target_euler = 0 (:495)
+    // attitude error: conj(q) (x) identity = (-x,-y,-z,w), no shortest wrap (:540-545)
+    float e0 = -x, e1 = -y, e2 = -z;
+    float r0 = cpsi * e0 + spsi * e1;  // inv(R_psi) (:551-557)
+    float r1 = -spsi * e0 + cpsi * e1;
+    rsp0 = tp.att[0] * r0; rsp1 = tp.att[1] * r1; rsp2 = tp.att[2] * e2;
+    // accel_error_body = R^T accel_e (:589) - uses the quaternion's own matrix, not the Euler one
+    nu[3] = R.m00 * aex + R.m10 * aey + R.m20 * aez;
+    nu[4] = R.m01 * aex + R.m11 * aey + R.m21 * aez;
+    nu[5] = R.m02 * aex + R.m12 * aey + R.m22 * aez;
+  }
+  m.lthrust = thrust;  // INDIControl.py:456 / INDIControl_6DOF.py:598
+  // ---- rate loop and allocation, ONCE for both laws: a warp that mixes quads and hexas runs them together instead of
+  // once per branch.  A quad's allocation matrix has zero columns 4, 5 and its nu[4] = nu[5] = 0, so the six-column
+  // product below is its pinv(G1 / 0.05) nu (INDIControl.py:459) exactly.
+  ds_rate_loop<EXT>(tp, s, inv_dt, acc_b, rsp0, rsp1, rsp2, m, nu);
+  if constexpr (!NU6) {
     ds_allocate_quad<NU6>(tp, nu, m, o);
   } else {
-    if constexpr (NU6) {
-      o.yaw_err = 0.f - psi;  // target_euler = 0 (:495)
-      // attitude error: conj(q) (x) identity = (-x,-y,-z,w), no shortest wrap (:540-545)
-      float e0 = -x, e1 = -y, e2 = -z;
-      float r0 = cpsi * e0 + spsi * e1;  // inv(R_psi) (:551-557)
-      float r1 = -spsi * e0 + cpsi * e1;
-      float nu[6];
-      ds_rate_loop<EXT>(tp, s, inv_dt, acc_b, tp.att[0] * r0, tp.att[1] * r1, tp.att[2] * e2, m, nu);
-      // accel_error_body = R^T accel_e (:589) - uses the quaternion's own matrix, not the Euler one
-      nu[3] = R.m00 * aex + R.m10 * aey + R.m20 * aez;
-      nu[4] = R.m01 * aex + R.m11 * aey + R.m21 * aez;
-      nu[5] = R.m02 * aex + R.m12 * aey + R.m22 * aez;
-      m.lthrust = thrust;  // :598
-      // ---- allocation: first WLS iteration in closed form, du = M nu (rotor pairs on packed instructions)
-      f2 du2[3];
-      bool feasible = true;
+    // 6-DOF law: first WLS iteration in closed form, du = M nu (rotor pairs on packed instructions)
+    f2 du2[3];
+    bool feasible = true;
 #pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        f2 d = ld2(tp.alloc2[p][0]) * nu[0];
+    for (int p = 0; p < 3; ++p) {
+      f2 d = ld2(tp.alloc2[p][0]) * nu[0];
 #pragma unroll
-        for (int j = 1; j < 6; ++j) d = ds_fma(ld2(tp.alloc2[p][j]), nu[j], d);
-        du2[p] = d;
-        // wls_alloc.py:264 decides u_opt >= umax + 1 or u_opt <= umin - 1 in FP64; the FP32 first iterate is trusted only
-        // when it clears the thresholds by DS_WLS_MARGIN (>> its rounding error), anything closer goes to the FP64
-        // active-set routine, whose own first pass repeats the reference's test exactly
-        const f2 c = f2_make(m.cmd[2 * p], m.cmd[2 * p + 1]);
-        const f2 hi = (ld2(tp.phi[p]) + (1.0f - DS_WLS_MARGIN)) - c, lo = (ld2(tp.plo[p]) - (1.0f - DS_WLS_MARGIN)) - c;
-        feasible = feasible && (f2_lo(d) < f2_lo(hi)) && (f2_lo(d) > f2_lo(lo)) && (f2_hi(d) < f2_hi(hi)) && (f2_hi(d) > f2_hi(lo));
-      }
-      o.wls_iter = 1;
-      if (DEFER) {
-        if (!feasible) {  // rare: hold the command now, ds_wls_fixup_kernel applies the active-set solution
-          o.wls_iter = 2;
-          if (wq->vehicle >= 0) {
-            const int qi = atomicAdd(wq->count, 1);
-            wq->index[qi] = wq->vehicle;
-            float* dst = wq->nu + (size_t)wq->vehicle * 6;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) dst[i] = nu[i];
-          }
-#pragma unroll
-          for (int p = 0; p < 3; ++p) du2[p] = f2_make(0.f, 0.f);
-        }
-      } else if (!feasible) {  // rare: run the active-set iterations in FP64
-        const DsWlsDev* P = wls_tab + type_id;
-        double v[6], umin[6], umax[6], u[6];
-        for (int i = 0; i < 6; ++i) {
-          v[i] = (double)nu[i];
-          umin[i] = P->pmin[i] - (double)m.cmd[i];
-          umax[i] = P->pmax[i] - (double)m.cmd[i];
-          u[i] = 0.0;
-        }
-        int it = ds_wls_alloc(P, v, umin, umax, u);
-        o.wls_iter = it;
-        for (int p = 0; p < 3; ++p)  // non-convergence: hold the command
-          du2[p] = (it > 0) ? f2_make((float)u[2 * p], (float)u[2 * p + 1]) : f2_make(0.f, 0.f);
-      }
-      ds_allocate<true, 6>(tp, nu, m, o, du2);  // cmd = clip(cmd + du) (:630-631)
+      for (int j = 1; j < 6; ++j) d = ds_fma(ld2(tp.alloc2[p][j]), nu[j], d);
+      du2[p] = d;
+      // wls_alloc.py:264 decides u_opt >= umax + 1 or u_opt <= umin - 1 in FP64; the FP32 first iterate is trusted only
+      // when it clears the thresholds by DS_WLS_MARGIN (>> its rounding error), anything closer goes to the FP64
+      // active-set routine, whose own first pass repeats the reference's test exactly
+      const f2 c = f2_make(m.cmd[2 * p], m.cmd[2 * p + 1]);
+      const f2 hi = (ld2(tp.phi[p]) + (1.0f - DS_WLS_MARGIN)) - c, lo = (ld2(tp.plo[p]) - (1.0f - DS_WLS_MARGIN)) - c;
+      feasible = feasible && (f2_lo(d) < f2_lo(hi)) && (f2_lo(d) > f2_lo(lo)) && (f2_hi(d) < f2_hi(hi)) && (f2_hi(d) > f2_hi(lo));
     }
+    feasible = feasible || !six;  // the quad law clips, it has no feasibility notion (INDIControl.py:486-487)
+    if (six) o.wls_iter = 1;
+    if (DEFER) {
+      if (!feasible) {  // rare: hold the command now, ds_wls_fixup_kernel applies the active-set solution
+        o.wls_iter = 2;
+        if (wq->vehicle >= 0) {
+          const int qi = atomicAdd(wq->count, 1);
+          wq->index[qi] = wq->vehicle;
+          float* dst = wq->nu + (size_t)wq->vehicle * 6;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) dst[i] = nu[i];
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) du2[p] = f2_make(0.f, 0.f);
+      }
+    } else if (!feasible) {  // rare: run the active-set iterations in FP64
+      const DsWlsDev* P = wls_tab + type_id;
+      double v[6], umin[6], umax[6], u[6];
+      for (int i = 0; i < 6; ++i) {
+        v[i] = (double)nu[i];
+        umin[i] = P->pmin[i] - (double)m.cmd[i];
+        umax[i] = P->pmax[i] - (double)m.cmd[i];
+        u[i] = 0.0;
+      }
+      int it = ds_wls_alloc(P, v, umin, umax, u);
+      o.wls_iter = it;
+      for (int p = 0; p < 3; ++p)  // non-convergence: hold the command
+        du2[p] = (it > 0) ? f2_make((float)u[2 * p], (float)u[2 * p + 1]) : f2_make(0.f, 0.f);
+    }
+    ds_allocate<true, 6>(tp, nu, m, o, du2);  // cmd = clip(cmd + du) (:630-631 / INDIControl.py:486-487)
   }
 }

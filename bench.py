@@ -87,7 +87,7 @@ def workload_config(envs_per_gpu: int, n_gpus: int) -> dict:
 class ClockSampler(threading.Thread):
     """nvidia-smi-equivalent clock / throttle-reason samples (NVML) taken DURING the timed regions."""
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.025):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.power = [], set(), []
@@ -95,46 +95,65 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
         self.error = None
 
+    def _open(self):
+        """NVML handle and constants, on the caller's thread BEFORE the timed region starts (the import and nvmlInit take
+        longer than a short timed region)."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                idx = self.index
+        self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+        self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        self._names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+
+    def _sample(self, with_power: bool):
+        nv, h = self._nv, self._h
+        clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.samples.append((clk, 0))
+        if with_power:  # a slower driver call: only on every eighth sample
+            try:
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+        for k, bit in self._names.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def start(self):
+        try:
+            self._open()
+        except Exception as e:  # NVML missing: report, do not fail the bench
+            self.error = repr(e)
+            return
+        super().start()
+
     def run(self):
         try:
-            import pynvml as nv
-
-            nv.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = self.index
-            if vis:
-                try:
-                    idx = int(vis.split(",")[self.index])
-                except Exception:
-                    idx = self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
-            }
+            n = 0
             while not self._halt.is_set():
-                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
-                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((clk, util))
-                try:
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                except Exception:
-                    pass
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
+                self._sample(n % 8 == 0)
+                n += 1
                 time.sleep(self.period)
-        except Exception as e:  # NVML missing: report, do not fail the bench
+        except Exception as e:
             self.error = repr(e)
 
     def stop(self) -> dict:
         self._halt.set()
-        self.join(timeout=2.0)
+        if self.is_alive():
+            self.join(timeout=2.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "error": self.error}
         clk = sorted(c for c, _ in self.samples)

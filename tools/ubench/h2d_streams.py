@@ -1,5 +1,11 @@
-import torch, time, os, sys
-sys.path.insert(0, '/root/repo')
+"""Pinned-memory H2D bandwidth of ONE GPU by stream count and piece size (is the e2e path of bench.py at the link's limit?).
+    python tools/ubench/h2d_streams.py   ->  profiles/r02_h2d_streams.txt"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 try:
     import bench
     print("numa:", bench.bind_to_gpu_numa_node(0))

@@ -1416,3 +1416,40 @@ def test_redzones_detect_a_stray_store():
         with pytest.raises(RuntimeError):  # DS_ERR_UNSUPPORTED: the handle has no guard bands
             plain.check_redzones()
         plain.close()
+
+
+# ------------------------------------------------------------------------------------------
+# one process driving two GPUs: every entry point runs on its handle's device and puts the caller's current device back
+# (runs where the box has >= 2 GPUs: gpurun --gpus 2)
+# ------------------------------------------------------------------------------------------
+def test_two_devices_in_one_process_keep_the_callers_current_device():
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dronesim_b200.core import SwarmCore
+    from dronesim_b200.workloads import hetero16
+
+    E = 40
+    models, K, flags, pos0, act0, tgt = hetero16(E, seed=1)
+    torch.cuda.set_device(0)
+    cores = [SwarmCore(models, E, aggregate_phy_steps=K, stats=True, device=d, **flags) for d in (0, 1)]
+    assert torch.cuda.current_device() == 0
+    for c in cores:
+        c.reset(pos0, action0=act0)
+        assert torch.cuda.current_device() == 0
+    tg = [c.targets_per_vehicle(tgt) for c in cores]
+    for step in range(10):  # interleaved launches on the two devices
+        for c, t in zip(cores, tg):
+            c.step(t, 1)
+            assert torch.cuda.current_device() == 0
+    for d in (0, 1):
+        torch.cuda.synchronize(d)
+    v0, v1 = cores[0].views(), cores[1].views()
+    assert v0["pos"].device.index == 0 and v1["pos"].device.index == 1
+    for k in ("pos", "quat", "vel", "omega_body", "cmd0123", "cmd45"):
+        np.testing.assert_array_equal(v0[k].cpu().numpy(), v1[k].cpu().numpy(), err_msg=k)  # same swarm, same bits
+    assert cores[1].stats()["non_finite"] == 0 and torch.cuda.current_device() == 0
+    x = torch.zeros(4, device="cuda")  # "cuda" still means device 0 for the caller
+    assert x.device.index == 0
+    for c in cores:
+        c.close()

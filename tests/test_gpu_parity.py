@@ -1453,3 +1453,72 @@ def test_two_devices_in_one_process_keep_the_callers_current_device():
     assert x.device.index == 0
     for c in cores:
         c.close()
+
+
+# ------------------------------------------------------------------------------------------
+# randomized configurations: swarm composition, add-on flags, substeps per control step, integrator, target mode and floor are
+# drawn from a seeded generator, so that the kernel-variant dispatch (homogeneous / mixed, compile-time / run-time add-ons,
+# centre-of-mass offsets, warp / block synchronised downwash, symmetric pairs) is exercised beyond the hand-picked cases
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", list(range(96)))
+def test_random_configuration_vs_oracle(seed):
+    _need_gpu()
+    rng = np.random.default_rng(1000 + seed)
+    pool = ["robobee", "tello", "hexa_6DOF", "hexa_6DOF_simple"]
+    D = int(rng.choice([1, 1, 2, 3, 4, 5, 8, 16]))
+    if rng.random() < 0.35:
+        models = [str(rng.choice(pool))] * D  # homogeneous swarm
+    else:
+        models = [str(m) for m in rng.choice(pool, D)]
+    integ = "rpy" if rng.random() < 0.25 else "quat"
+    gnd, drag = bool(rng.random() < 0.5), bool(rng.random() < 0.5)
+    dw = bool(D > 1 and rng.random() < 0.6)
+    K = int(rng.choice([1, 2, 5, 8]))
+    E = int(rng.choice([1, 3, 9])) if D * 9 <= 80 else int(rng.choice([1, 2, 3]))
+    floor = bool(integ == "quat" and rng.random() < 0.2)
+    kw = dict(ground_plane_z=0.9) if floor else {}
+    ext = {}
+    if integ == "quat" and seed >= 32 and rng.random() < 0.3:  # extensions beyond the reference: motor lag, filtered ang. acc.
+        ext = dict(motor_tau=float(rng.choice([0.0, 0.02])), acc_filter_hz=float(rng.choice([0.0, 30.0])))
+    core, orc = make_pair(models, E, integ, K=K, gnd=gnd, drag=drag, dw=dw, stats=True, **ext, **kw)
+    if floor:
+        orc.floor_z = 0.9
+    slot = np.arange(D)
+    pos0 = np.zeros((E, D, 3))
+    pos0[..., 0], pos0[..., 1] = 1.1 * (slot % 4), 1.1 * (slot // 4)
+    pos0[..., 2] = 1.0 + 0.3 * slot
+    pos0 += rng.uniform(-0.03, 0.03, pos0.shape)
+    act0 = np.zeros((E, D, 6))
+    for s, m in enumerate(models):
+        act0[:, s, : (6 if "hexa" in m else 4)] = 0.45 if "hexa" in m else 0.4
+    core.reset(pos0, action0=act0)
+    orc.reset(pos0)
+    table_mode = bool(rng.random() < 0.4)
+    tgt_pos = pos0 + rng.uniform(-0.2, 0.2, pos0.shape)
+    T = 6
+    if table_mode:
+        tab = np.zeros((5, 10))
+        tab[:, 0:3] = rng.uniform(-0.1, 0.1, (5, 3))
+        tab[:, 3:6] = rng.uniform(-0.2, 0.2, (5, 3))
+        tab[:, 9] = rng.uniform(-0.3, 0.3, 5)
+        tg = core.targets_table(tab, offset=np.concatenate([tgt_pos.reshape(-1, 3), np.zeros((E * D, 1))], axis=1))
+    else:
+        yaw = rng.uniform(-0.3, 0.3, (E, D))
+        tg = core.targets_per_vehicle(np.concatenate([tgt_pos.reshape(-1, 3), yaw.reshape(-1, 1)], axis=1))
+    act = act0.copy()
+    wp = np.zeros((E, D), dtype=np.int64)
+    for _ in range(T):
+        core.step(tg, 1)
+        orc.physics_step(act)
+        if table_mode:
+            act = orc.control_step(tgt_pos + tab[wp, 0:3], tvel=tab[wp, 3:6], tacc=tab[wp, 6:9], tyaw=tab[wp, 9])
+            wp = np.where(wp < 4, wp + 1, 0)
+        else:
+            act = orc.control_step(tgt_pos, tyaw=yaw)
+    what = "seed %d: %s E=%d K=%d %s gnd=%d drag=%d dw=%d floor=%d table=%d ext=%s" % (seed, models, E, K, integ, gnd, drag, dw, floor, table_mode, ext)
+    _compare_state(core, orc, pos_tol=5e-5, att_tol=5e-5, what=what)
+    st = core_state(core)
+    cmd = np.concatenate([st["cmd0123"], st["cmd45"]], axis=1)
+    np.testing.assert_allclose(cmd, act.reshape(-1, 6), atol=2e-4, err_msg=what)
+    assert core.stats()["non_finite"] == 0, what
+    core.close()
